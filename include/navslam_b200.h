@@ -1,0 +1,157 @@
+/*
+ * navslam_b200.h -- C ABI of libnavslam_b200.so, the sm_100a CUDA implementation of
+ * NAV-SLAM's data-parallel front end (reference: wuHakureReimu/NAV-SLAM).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  The
+ * image shape is a run-time argument here; the reference bakes MAX_ROWS/MAX_COLS into
+ * its signatures (utils/pointcloud.h:9-10), so the symbols the reference's main.c binds
+ * (init_slam, slam_localization, slam_mapping, convertToPointCloud, buildKDTree, ...) are
+ * exported with byte-identical signatures by the per-shape shim built from
+ * nav-slam_b200/shim/navslam_shim.c on top of this library (see include/navslam_ref_abi.h
+ * and INTEGRATION.md).
+ *
+ * Conventions
+ *   - every function returning int returns 0 on success, non-zero on failure;
+ *     nav_last_error() then describes the failure (thread-local).  There is no CPU
+ *     fallback anywhere: without a CUDA device nav_create()/nav_kdtree_build() fail.
+ *   - "host" arguments are ordinary host pointers (pageable or pinned; pinned memory,
+ *     e.g. from nav_host_alloc, is DMA'd directly, pageable memory is staged).
+ *     "dev" arguments are device pointers on the context's device.
+ *   - points are the reference's `Point` (3 x double, 24 B, utils/pointcloud.h:39-44),
+ *     clouds are row-major [rows][cols] arrays of points WITHOUT the 8-byte PointCloud
+ *     header (pass &cloud->ToF_position[0][0]).
+ *   - labels are the reference's `int feature[rows][cols]` (src/slam.c:11): 1 = edge.
+ *   - nearest-neighbour answers are exact: idx = the LOWEST index among the points that
+ *     attain the minimum of dsq = (dx*dx + dy*dy) + dz*dz evaluated in binary64 without
+ *     FMA (the reference's arithmetic, utils/kdtree.c:14-17), dist = sqrt(dsq).  The
+ *     reference returns the first such point its DFS visits (utils/kdtree.c:117); the two
+ *     differ only when two distinct points are at exactly the same distance.
+ */
+#ifndef NAVSLAM_B200_H
+#define NAVSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double x, y, z; } nav_point;                          /* Point,  utils/pointcloud.h:39-44 */
+typedef struct { double x, y, z, roll, pitch, yaw; } nav_pos;          /* Pos (mm, degrees), utils/pointcloud.h:32-35 */
+typedef struct { nav_point ori, nearest; double distance; } nav_corr;  /* NeighborResult, utils/kdtree.h:14-18 */
+
+typedef struct nav_ctx nav_ctx;       /* one image shape on one device */
+typedef struct nav_kdtree nav_kdtree; /* device-resident flat kd-tree  */
+
+/* ---- library ------------------------------------------------------------------- */
+const char *nav_version(void);
+const char *nav_last_error(void);
+int nav_device_count(void);          /* 0 when no CUDA device is usable */
+void *nav_host_alloc(size_t bytes);  /* pinned host memory (cudaHostAlloc) */
+void nav_host_free(void *p);
+
+/* ---- context ------------------------------------------------------------------- */
+/* n_seq = number of independent sequences processed side by side (1..NAV_MAX_SEQ);
+ * every cloud/label/global argument of the frame calls below then holds n_seq images
+ * back to back.  Returns NULL on failure (no device, shape unsupported). */
+#define NAV_MAX_SEQ 16
+nav_ctx *nav_create(int rows, int cols, int device, int n_seq);
+void nav_destroy(nav_ctx *ctx);
+int nav_rows(const nav_ctx *ctx);
+int nav_cols(const nav_ctx *ctx);
+int nav_set_stream(nav_ctx *ctx, void *cuda_stream); /* run on the caller's cudaStream_t (NULL = own stream) */
+int nav_synchronize(nav_ctx *ctx);
+/* number of kernels this library has launched on behalf of ctx since creation */
+uint64_t nav_launch_count(const nav_ctx *ctx);
+
+/* ---- function-level mirrors, HOST buffers (one image each) ------------------------ */
+/* replaces convertToPointCloud, utils/pointcloud.c:8 (utils/pointcloud.h:55) */
+int nav_convert_to_pointcloud(nav_ctx *ctx, const int *distances, nav_point *cloud_out);
+/* replaces extract_feature, src/slam.c:11: sets feature[i]=1 where curvature > 0.1, never writes 0 */
+int nav_extract_feature(nav_ctx *ctx, const nav_point *cloud, int *feature);
+/* the curvature extract_feature thresholds (binary64, reference association order); 0 on the
+ * two border columns each side.  The reference does not return it; exposed for parity tests. */
+int nav_curvature(nav_ctx *ctx, const nav_point *cloud, double *curvature_out);
+/* replaces flattenPoints, src/slam.c:64: stable compaction of one row where row_feature == 1 */
+int nav_flatten_points(nav_ctx *ctx, const nav_point *row_points, const int *row_feature,
+                       nav_point *flattened_out, size_t *num_points_out);
+/* the per-point rigid transform of src/slam.c:145-160,402-416: out = pos.xyz + R(pos.rpy deg) * p */
+int nav_transform_cloud(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos, nav_point *global_out);
+
+/* ---- kd-tree, replaces utils/kdtree.h:21-27 ---------------------------------------- */
+/* Build from n host points (the caller's array is NOT permuted; idx refers to it). */
+nav_kdtree *nav_kdtree_build(int device, const nav_point *points, size_t n);
+nav_kdtree *nav_kdtree_build_dev(int device, const void *dev_points, size_t n, void *cuda_stream);
+void nav_kdtree_free(nav_kdtree *tree);
+size_t nav_kdtree_size(const nav_kdtree *tree);
+/* batched exact 1-NN.  idx[i] = -1 and dist[i] = +inf for an empty tree.  nearest_out may be NULL. */
+int nav_kdtree_nn_batch(nav_kdtree *tree, const nav_point *queries, size_t nq,
+                        int32_t *idx_out, double *dist_out, nav_point *nearest_out);
+int nav_kdtree_nn_batch_dev(nav_kdtree *tree, const void *dev_queries, size_t nq,
+                            void *dev_idx_out, void *dev_dist_out, void *cuda_stream);
+/* exact brute-force baseline on the same contract (tensor-core candidate tiles + exact re-rank
+ * when use_tensor_cores != 0, plain fp64 scan otherwise) */
+int nav_bruteforce_nn_batch_dev(int device, const void *dev_points, size_t n, const void *dev_queries,
+                                size_t nq, void *dev_idx_out, void *dev_dist_out,
+                                int use_tensor_cores, void *cuda_stream);
+/* copy the flat node array out for inspection: nodes_out[n] points in storage (in-order) layout,
+ * orig_idx_out[n] their indices in the build input */
+int nav_kdtree_export(nav_kdtree *tree, nav_point *nodes_out, int32_t *orig_idx_out);
+uint64_t nav_kdtree_launch_count(const nav_kdtree *tree);
+
+/* ---- SLAM step, HOST buffers; replaces headers/slam.h:22-28 -------------------------- */
+/* init_slam (src/slam.c:134): global_out = pose(cloud); builds the per-row map of frame 0. */
+int nav_slam_init(nav_ctx *ctx, const nav_pos *pos, const nav_point *cloud, nav_point *global_out);
+/* the matching half of slam_localization (src/slam.c:180-284): labels, query transform, per-row
+ * exact NN against the previous frame's labelled points, per-row dedupe.  corr_out receives up to
+ * corr_cap entries in the reference's order; *n_corr_out the number found. */
+int nav_slam_match(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos_predict,
+                   const nav_pos *pos_last, nav_corr *corr_out, size_t corr_cap, size_t *n_corr_out);
+/* whole slam_localization (src/slam.c:178-390): nav_slam_match + the reference's 200-iteration
+ * translation-only Adam fit on the host.  verbose != 0 prints the reference's per-iteration lines. */
+int nav_slam_localization(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos_predict,
+                          const nav_pos *pos_last, nav_pos *pos_out, double *error_out, int verbose);
+/* slam_mapping (src/slam.c:393): global_out = pose(cloud), per-row map for the next frame.
+ * cloud == NULL reuses the cloud (and labels) of the preceding nav_slam_match/localization call. */
+int nav_slam_mapping(nav_ctx *ctx, const nav_pos *pos, const nav_point *cloud, nav_point *global_out);
+/* one front-end frame with raw per-pixel outputs (SURVEY 8d "one frame of work"): labels, queries,
+ * NN vs the previous frame, then mapping with pos_final.  nn_idx = flat pixel (row*cols+col) of the
+ * match in the previous frame, -1 if unlabelled or the row's map is empty; nn_dist = -1 if
+ * unlabelled, +inf if the map is empty.  Any output pointer may be NULL. */
+int nav_frontend_frame(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos_predict,
+                       const nav_pos *pos_last, const nav_pos *pos_final, int *feature_out,
+                       int32_t *nn_idx_out, double *nn_dist_out, nav_point *global_out);
+
+/* ---- device-resident entry points (inputs already in HBM) ------------------------------ */
+/* labels for n_images images [n_images][rows][cols] in one launch (pose independent) */
+int nav_extract_feature_batch_dev(nav_ctx *ctx, const void *dev_clouds, size_t n_images,
+                                  void *dev_labels_out);
+/* nav_frontend_frame on device data: dev_cloud holds n_seq images; poses are n_seq-long host arrays;
+ * results stay in the context (nav_frame_results_dev) */
+int nav_frontend_frame_dev(nav_ctx *ctx, const void *dev_cloud, const nav_pos *pos_predict,
+                           const nav_pos *pos_last, const nav_pos *pos_final);
+int nav_slam_init_dev(nav_ctx *ctx, const void *dev_cloud, const nav_pos *pos);
+typedef struct {
+    void *labels;   /* int32  [n_seq][rows][cols] */
+    void *nn_idx;   /* int32  [n_seq][rows][cols] */
+    void *nn_dist;  /* double [n_seq][rows][cols] */
+    void *global;   /* point  [n_seq][rows][cols] */
+    void *map_count;/* int32  [n_seq][rows]  labelled points per row of the frame just mapped */
+} nav_frame_results;
+int nav_frame_results_dev(nav_ctx *ctx, nav_frame_results *out);
+
+/* copy out the map the context holds for one (sequence,row): the labelled global points of the
+ * frame mapped last, compacted in column order (= the flattenedPoints array of src/slam.c:170-171),
+ * and the column each came from.  pts_out needs room for cols points; col_out may be NULL. */
+int nav_row_map_export(nav_ctx *ctx, int seq, int row, nav_point *pts_out, int32_t *col_out, size_t *n_out);
+
+/* per-kernel device time accumulated with CUDA events on the context's stream (enable first) */
+int nav_profile_enable(nav_ctx *ctx, int on);
+/* name = "labels" | "match" | "map"; returns accumulated ms and launches since the last reset */
+int nav_profile_read(nav_ctx *ctx, const char *name, double *ms_out, uint64_t *launches_out, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,348 @@
+"""ctypes binding of include/navslam_b200.h -- used by tests, bench.py and smoke().
+
+The product is the C-ABI library (libnavslam_b200.so) and the per-shape reference shims; this
+module is only a thin caller.  It FAILS LOUDLY when the CUDA library is missing or no device is
+visible: there is no CPU fallback and nothing here imports oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+c_i32_p = C.POINTER(C.c_int32)
+
+
+class NavPos(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("x", "y", "z", "roll", "pitch", "yaw")]
+
+
+class NavFrameResults(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("labels", "nn_idx", "nn_dist", "global_", "map_count")]
+
+
+class NavError(RuntimeError):
+    pass
+
+
+_LIB = None
+
+# every symbol include/navslam_b200.h declares (tests check the .so exports all of them)
+EXPORTS = [
+    "nav_version", "nav_last_error", "nav_device_count", "nav_host_alloc", "nav_host_free",
+    "nav_create", "nav_destroy", "nav_rows", "nav_cols", "nav_set_stream", "nav_synchronize",
+    "nav_launch_count", "nav_convert_to_pointcloud", "nav_extract_feature", "nav_curvature",
+    "nav_flatten_points", "nav_transform_cloud", "nav_kdtree_build", "nav_kdtree_build_dev",
+    "nav_kdtree_free", "nav_kdtree_size", "nav_kdtree_nn_batch", "nav_kdtree_nn_batch_dev",
+    "nav_bruteforce_nn_batch_dev", "nav_kdtree_export", "nav_kdtree_launch_count", "nav_slam_init",
+    "nav_slam_match", "nav_slam_localization", "nav_slam_mapping", "nav_frontend_frame",
+    "nav_extract_feature_batch_dev", "nav_frontend_frame_dev", "nav_slam_init_dev",
+    "nav_frame_results_dev", "nav_profile_enable", "nav_profile_read", "nav_row_map_export",
+]
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load_library(build_if_missing: bool = True):
+    """dlopen libnavslam_b200.so (building it with nvcc if it is absent)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise NavError(f"{path} is missing: run __graft_entry__.build() (needs nvcc)")
+        _build.build_library()
+    L = C.CDLL(path)
+    L.nav_version.restype = C.c_char_p
+    L.nav_last_error.restype = C.c_char_p
+    L.nav_host_alloc.restype = C.c_void_p
+    L.nav_host_alloc.argtypes = [C.c_size_t]
+    L.nav_host_free.argtypes = [C.c_void_p]
+    L.nav_create.restype = C.c_void_p
+    L.nav_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.nav_destroy.argtypes = [C.c_void_p]
+    L.nav_rows.argtypes = [C.c_void_p]
+    L.nav_cols.argtypes = [C.c_void_p]
+    L.nav_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.nav_synchronize.argtypes = [C.c_void_p]
+    L.nav_launch_count.restype = C.c_uint64
+    L.nav_launch_count.argtypes = [C.c_void_p]
+    vp = C.c_void_p
+    L.nav_convert_to_pointcloud.argtypes = [vp, vp, vp]
+    L.nav_extract_feature.argtypes = [vp, vp, vp]
+    L.nav_curvature.argtypes = [vp, vp, vp]
+    L.nav_flatten_points.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_size_t)]
+    L.nav_transform_cloud.argtypes = [vp, vp, C.POINTER(NavPos), vp]
+    L.nav_kdtree_build.restype = vp
+    L.nav_kdtree_build.argtypes = [C.c_int, vp, C.c_size_t]
+    L.nav_kdtree_build_dev.restype = vp
+    L.nav_kdtree_build_dev.argtypes = [C.c_int, vp, C.c_size_t, vp]
+    L.nav_kdtree_free.argtypes = [vp]
+    L.nav_kdtree_size.restype = C.c_size_t
+    L.nav_kdtree_size.argtypes = [vp]
+    L.nav_kdtree_launch_count.restype = C.c_uint64
+    L.nav_kdtree_launch_count.argtypes = [vp]
+    L.nav_kdtree_nn_batch.argtypes = [vp, vp, C.c_size_t, vp, vp, vp]
+    L.nav_kdtree_nn_batch_dev.argtypes = [vp, vp, C.c_size_t, vp, vp, vp]
+    L.nav_bruteforce_nn_batch_dev.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp, vp, C.c_int, vp]
+    L.nav_kdtree_export.argtypes = [vp, vp, vp]
+    L.nav_slam_init.argtypes = [vp, C.POINTER(NavPos), vp, vp]
+    L.nav_slam_init_dev.argtypes = [vp, vp, C.POINTER(NavPos)]
+    L.nav_slam_match.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), vp, C.c_size_t,
+                                 C.POINTER(C.c_size_t)]
+    L.nav_slam_localization.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
+                                        c_double_p, C.c_int]
+    L.nav_slam_mapping.argtypes = [vp, C.POINTER(NavPos), vp, vp]
+    L.nav_frontend_frame.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
+                                     vp, vp, vp, vp]
+    L.nav_extract_feature_batch_dev.argtypes = [vp, vp, C.c_size_t, vp]
+    L.nav_frontend_frame_dev.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos)]
+    L.nav_frame_results_dev.argtypes = [vp, C.POINTER(NavFrameResults)]
+    L.nav_row_map_export.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_size_t)]
+    L.nav_profile_enable.argtypes = [vp, C.c_int]
+    L.nav_profile_read.argtypes = [vp, C.c_char_p, c_double_p, C.POINTER(C.c_uint64), C.c_int]
+    _LIB = L
+    return L
+
+
+def _check(rc, L):
+    if rc != 0:
+        raise NavError(L.nav_last_error().decode("utf-8", "replace"))
+
+
+def _pos_array(p, n=1):
+    """nav_pos[n] from an (n,6) / (6,) array-like."""
+    a = np.ascontiguousarray(p, dtype=np.float64).reshape(-1, 6)
+    assert a.shape[0] == n, (a.shape, n)
+    arr = (NavPos * n)()
+    for i in range(n):
+        arr[i] = NavPos(*[float(v) for v in a[i]])
+    return arr
+
+
+def _pts(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    assert a.shape[-1] == 3
+    return a
+
+
+class Context:
+    """nav_ctx: one image shape (rows x cols), n_seq sequences side by side, on one device."""
+
+    def __init__(self, rows: int, cols: int, device: int = 0, n_seq: int = 1):
+        self.L = load_library()
+        self.rows, self.cols, self.n_seq, self.device = rows, cols, n_seq, device
+        self.h = self.L.nav_create(rows, cols, device, n_seq)
+        if not self.h:
+            raise NavError(self.L.nav_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.nav_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- function level (host buffers)
+    def convert_to_pointcloud(self, distances):
+        d = np.ascontiguousarray(distances, dtype=np.int32).reshape(self.rows, self.cols)
+        out = np.empty((self.rows, self.cols, 3))
+        _check(self.L.nav_convert_to_pointcloud(self.h, d.ctypes.data, out.ctypes.data), self.L)
+        return out
+
+    def extract_feature(self, cloud, feature=None):
+        cloud = _pts(cloud)
+        if feature is None:
+            feature = np.zeros((self.rows, self.cols), dtype=np.int32)
+        assert feature.dtype == np.int32 and feature.flags.c_contiguous
+        _check(self.L.nav_extract_feature(self.h, cloud.ctypes.data, feature.ctypes.data), self.L)
+        return feature
+
+    def curvature(self, cloud):
+        cloud = _pts(cloud)
+        out = np.empty((self.rows, self.cols))
+        _check(self.L.nav_curvature(self.h, cloud.ctypes.data, out.ctypes.data), self.L)
+        return out
+
+    def flatten_points(self, row_points, row_feature):
+        row_points = _pts(row_points)
+        feat = np.ascontiguousarray(row_feature, dtype=np.int32)
+        out = np.empty_like(row_points)
+        n = C.c_size_t(0)
+        _check(self.L.nav_flatten_points(self.h, row_points.ctypes.data, feat.ctypes.data, out.ctypes.data,
+                                         C.byref(n)), self.L)
+        return out[:n.value].copy()
+
+    def transform_cloud(self, cloud, pos):
+        cloud = _pts(cloud)
+        out = np.empty_like(cloud)
+        _check(self.L.nav_transform_cloud(self.h, cloud.ctypes.data, _pos_array(pos), out.ctypes.data), self.L)
+        return out
+
+    # ---- SLAM step (host buffers)
+    def slam_init(self, pos, cloud, want_global=True):
+        cloud = _pts(cloud)
+        g = np.empty_like(cloud) if want_global else None
+        _check(self.L.nav_slam_init(self.h, _pos_array(pos, self.n_seq), cloud.ctypes.data,
+                                    g.ctypes.data if g is not None else None), self.L)
+        return g
+
+    def slam_match(self, cloud, pos_predict, pos_last):
+        cloud = _pts(cloud)
+        cap = self.rows * self.cols
+        corr = np.empty((cap, 7))
+        n = C.c_size_t(0)
+        _check(self.L.nav_slam_match(self.h, cloud.ctypes.data, _pos_array(pos_predict), _pos_array(pos_last),
+                                     corr.ctypes.data, cap, C.byref(n)), self.L)
+        return corr[:n.value].copy()
+
+    def slam_localization(self, cloud, pos_predict, pos_last, verbose=False):
+        cloud = _pts(cloud)
+        out = NavPos()
+        err = C.c_double(0)
+        _check(self.L.nav_slam_localization(self.h, cloud.ctypes.data, _pos_array(pos_predict),
+                                            _pos_array(pos_last), C.byref(out), C.byref(err),
+                                            1 if verbose else 0), self.L)
+        return np.array([out.x, out.y, out.z, out.roll, out.pitch, out.yaw]), err.value
+
+    def slam_mapping(self, pos, cloud=None, want_global=True):
+        shape = (self.rows, self.cols, 3) if self.n_seq == 1 else (self.n_seq, self.rows, self.cols, 3)
+        g = np.empty(shape) if want_global else None
+        cp = None
+        if cloud is not None:
+            cloud = _pts(cloud)
+            cp = cloud.ctypes.data
+        _check(self.L.nav_slam_mapping(self.h, _pos_array(pos, self.n_seq), cp,
+                                       g.ctypes.data if g is not None else None), self.L)
+        return g
+
+    def frontend_frame(self, cloud, pos_predict, pos_last, pos_final):
+        cloud = _pts(cloud)
+        shp = cloud.shape[:-1]
+        feat = np.empty(shp, dtype=np.int32)
+        idx = np.empty(shp, dtype=np.int32)
+        dist = np.empty(shp)
+        g = np.empty_like(cloud)
+        n = self.n_seq
+        _check(self.L.nav_frontend_frame(self.h, cloud.ctypes.data, _pos_array(pos_predict, n),
+                                         _pos_array(pos_last, n), _pos_array(pos_final, n), feat.ctypes.data,
+                                         idx.ctypes.data, dist.ctypes.data, g.ctypes.data), self.L)
+        return feat, idx, dist, g
+
+    # ---- device resident (raw device pointers, e.g. torch tensor .data_ptr())
+    def set_stream(self, cuda_stream_handle):
+        _check(self.L.nav_set_stream(self.h, cuda_stream_handle), self.L)
+
+    def synchronize(self):
+        _check(self.L.nav_synchronize(self.h), self.L)
+
+    def extract_feature_batch_dev(self, dev_clouds_ptr, n_images, dev_labels_ptr):
+        _check(self.L.nav_extract_feature_batch_dev(self.h, dev_clouds_ptr, n_images, dev_labels_ptr), self.L)
+
+    def slam_init_dev(self, dev_cloud_ptr, pos):
+        _check(self.L.nav_slam_init_dev(self.h, dev_cloud_ptr, _pos_array(pos, self.n_seq)), self.L)
+
+    def frontend_frame_dev(self, dev_cloud_ptr, pos_predict, pos_last, pos_final):
+        n = self.n_seq
+        _check(self.L.nav_frontend_frame_dev(self.h, dev_cloud_ptr, _pos_array(pos_predict, n),
+                                             _pos_array(pos_last, n), _pos_array(pos_final, n)), self.L)
+
+    def frame_results_dev(self) -> NavFrameResults:
+        r = NavFrameResults()
+        _check(self.L.nav_frame_results_dev(self.h, C.byref(r)), self.L)
+        return r
+
+    def row_map_export(self, row, seq=0):
+        pts = np.empty((self.cols, 3))
+        col = np.empty(self.cols, dtype=np.int32)
+        n = C.c_size_t(0)
+        _check(self.L.nav_row_map_export(self.h, seq, row, pts.ctypes.data, col.ctypes.data, C.byref(n)), self.L)
+        return pts[:n.value].copy(), col[:n.value].copy()
+
+    def launch_count(self) -> int:
+        return int(self.L.nav_launch_count(self.h))
+
+    def profile_enable(self, on=True):
+        _check(self.L.nav_profile_enable(self.h, 1 if on else 0), self.L)
+
+    def profile_read(self, name, reset=False):
+        ms = C.c_double(0)
+        n = C.c_uint64(0)
+        _check(self.L.nav_profile_read(self.h, name.encode(), C.byref(ms), C.byref(n), 1 if reset else 0), self.L)
+        return ms.value, int(n.value)
+
+
+class KdTree:
+    """nav_kdtree: flat device-resident kd-tree over n points."""
+
+    def __init__(self, points=None, device: int = 0, *, dev_ptr=None, n=None, stream=None):
+        self.L = load_library()
+        self.device = device
+        if dev_ptr is not None:
+            self.h = self.L.nav_kdtree_build_dev(device, dev_ptr, n, stream)
+        else:
+            pts = _pts(points)
+            self._n = pts.shape[0]
+            self.h = self.L.nav_kdtree_build(device, pts.ctypes.data, pts.shape[0])
+        if not self.h:
+            raise NavError(self.L.nav_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.nav_kdtree_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def __len__(self):
+        return int(self.L.nav_kdtree_size(self.h))
+
+    def nn_batch(self, queries, want_nearest=True):
+        q = _pts(queries)
+        nq = q.shape[0]
+        idx = np.empty(nq, dtype=np.int32)
+        dist = np.empty(nq)
+        near = np.full((nq, 3), np.nan) if want_nearest else None
+        _check(self.L.nav_kdtree_nn_batch(self.h, q.ctypes.data, nq, idx.ctypes.data, dist.ctypes.data,
+                                          near.ctypes.data if near is not None else None), self.L)
+        return idx, dist, near
+
+    def nn_batch_dev(self, dev_q_ptr, nq, dev_idx_ptr, dev_dist_ptr, stream=None):
+        _check(self.L.nav_kdtree_nn_batch_dev(self.h, dev_q_ptr, nq, dev_idx_ptr, dev_dist_ptr, stream), self.L)
+
+    def export(self):
+        n = len(self)
+        nodes = np.empty((n, 3))
+        idx = np.empty(n, dtype=np.int32)
+        _check(self.L.nav_kdtree_export(self.h, nodes.ctypes.data, idx.ctypes.data), self.L)
+        return nodes, idx
+
+    def launch_count(self) -> int:
+        return int(self.L.nav_kdtree_launch_count(self.h))
+
+
+def bruteforce_nn_dev(device, dev_pts_ptr, n, dev_q_ptr, nq, dev_idx_ptr, dev_dist_ptr, use_tensor_cores=False,
+                      stream=None):
+    L = load_library()
+    _check(L.nav_bruteforce_nn_batch_dev(device, dev_pts_ptr, n, dev_q_ptr, nq, dev_idx_ptr, dev_dist_ptr,
+                                         1 if use_tensor_cores else 0, stream), L)
+
+
+def device_count() -> int:
+    return int(load_library().nav_device_count())

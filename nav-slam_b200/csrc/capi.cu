@@ -1,0 +1,917 @@
+// capi.cu -- the C ABI of libnavslam_b200.so (include/navslam_b200.h): contexts, host<->device
+// staging, and the host-side scalar pieces the reference keeps on the CPU (rotation matrix from
+// libm sin/cos, tan tables, the translation-only Adam fit of src/slam.c:218-379).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "nav_kdtree.cuh"
+#include "nav_kernels.cuh"
+
+using namespace nav;
+
+// ------------------------------------------------------------------ errors ------------------
+static thread_local char g_err[512] = "";
+
+static int fail(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CUP(call)                                                                             \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return nullptr;                                                                   \
+        }                                                                                     \
+    } while (0)
+
+extern "C" const char *nav_version(void) { return "navslam_b200 0.1 (sm_100a)"; }
+extern "C" const char *nav_last_error(void) { return g_err; }
+
+extern "C" int nav_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" void *nav_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        fail("cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void nav_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------ staging -----------------
+struct PendingOut {
+    void *dst;
+    const void *src;
+    size_t bytes;
+};
+
+struct Stager {
+    unsigned char *buf = nullptr;
+    size_t cap = 0, used = 0;
+    std::vector<PendingOut> pending;
+
+    static bool is_pinned(const void *p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return at.type == cudaMemoryTypeHost;
+    }
+    // staging space lives for one API call; growing needs the stream idle
+    unsigned char *take(size_t bytes, cudaStream_t stream) {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (used + bytes > cap) {
+            if (used != 0) return nullptr;  // caller reserves up front
+            cudaStreamSynchronize(stream);
+            if (buf) cudaFreeHost(buf);
+            buf = nullptr;
+            cap = 0;
+            if (cudaHostAlloc((void **)&buf, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+            cap = bytes;
+        }
+        unsigned char *p = buf + used;
+        used += bytes;
+        return p;
+    }
+    int reserve(size_t bytes, cudaStream_t stream) {
+        if (used != 0 || !pending.empty()) {  // a previous call bailed out half way
+            cudaStreamSynchronize(stream);
+            used = 0;
+            pending.clear();
+        }
+        if (bytes <= cap) return 0;
+        unsigned char *p = take(bytes, stream);
+        used = 0;
+        return p ? 0 : 1;
+    }
+    int h2d(void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+        if (bytes == 0) return 0;
+        const void *from = src;
+        if (!is_pinned(src)) {
+            unsigned char *s = take(bytes, stream);
+            if (!s) return 1;
+            memcpy(s, src, bytes);
+            from = s;
+        }
+        return cudaMemcpyAsync(dst, from, bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess;
+    }
+    int d2h(void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+        if (bytes == 0) return 0;
+        void *to = dst;
+        if (!is_pinned(dst)) {
+            unsigned char *s = take(bytes, stream);
+            if (!s) return 1;
+            pending.push_back({dst, s, bytes});
+            to = s;
+        }
+        return cudaMemcpyAsync(to, src, bytes, cudaMemcpyDeviceToHost, stream) != cudaSuccess;
+    }
+    int finish(cudaStream_t stream) {
+        cudaError_t e = cudaStreamSynchronize(stream);
+        for (auto &p : pending) memcpy(p.dst, p.src, p.bytes);
+        pending.clear();
+        used = 0;
+        return e != cudaSuccess;
+    }
+    void release() {
+        if (buf) cudaFreeHost(buf);
+        buf = nullptr;
+        cap = used = 0;
+    }
+};
+
+// ------------------------------------------------------------------ context -----------------
+struct ProfSlot {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    size_t used = 0;
+    double ms = 0;
+    uint64_t launches = 0;
+};
+
+struct nav_ctx {
+    int rows = 0, cols = 0, n_seq = 1, device = 0, sm_count = 148;
+    size_t npx = 0, ntot = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    double *d_cloud = nullptr, *d_global = nullptr, *d_curv = nullptr, *d_nn_dist = nullptr;
+    int *d_labels = nullptr, *d_nn_idx = nullptr;
+    RowMap map = {};
+    nav_corr *d_corr_rows = nullptr, *d_corr = nullptr;
+    int *d_corr_row_count = nullptr, *d_corr_total = nullptr;
+    int *d_dist = nullptr;
+    double *d_tan_col = nullptr, *d_tan_row = nullptr;
+    double *d_flat = nullptr;
+    int *d_flat_count = nullptr;
+    int *h_small = nullptr;  // pinned scratch for counts
+    Stager stage;
+    bool have_map = false, cloud_resident = false;
+    uint64_t launches = 0;
+    bool prof = false;
+    ProfSlot prof_labels, prof_match, prof_map;
+};
+
+static void rotation_from_pos(const nav_pos *pos, double R[9]) {
+    // DEG2RAD(x) = x * M_PI / 180.0 (src/slam.c:8), then src/slam.c:95-115 with the host libm
+    const double roll = pos->roll * M_PI / 180.0, pitch = pos->pitch * M_PI / 180.0,
+                 yaw = pos->yaw * M_PI / 180.0;
+    const double cr = cos(roll), sr = sin(roll), cp = cos(pitch), sp = sin(pitch), cy = cos(yaw),
+                 sy = sin(yaw);
+    R[0] = cy * cp;
+    R[1] = cy * sp * sr - sy * cr;
+    R[2] = cy * sp * cr + sy * sr;
+    R[3] = sy * cp;
+    R[4] = sy * sp * sr + cy * cr;
+    R[5] = sy * sp * cr - cy * sr;
+    R[6] = -sp;
+    R[7] = cp * sr;
+    R[8] = cp * cr;
+}
+
+static PoseXf make_pose(const nav_pos *pos, const nav_pos *last) {
+    PoseXf q;
+    rotation_from_pos(pos, q.R);
+    q.t[0] = pos->x;
+    q.t[1] = pos->y;
+    q.t[2] = pos->z;
+    // transform[0..2] = pos_predict - pos_last (src/slam.c:84-88)
+    q.shift[0] = last ? pos->x - last->x : 0.0;
+    q.shift[1] = last ? pos->y - last->y : 0.0;
+    q.shift[2] = last ? pos->z - last->z : 0.0;
+    return q;
+}
+
+struct ProfScope {
+    nav_ctx *c;
+    ProfSlot *s;
+    size_t slot = 0;
+    ProfScope(nav_ctx *ctx, ProfSlot *ps) : c(ctx), s(ps) {
+        if (!c->prof) return;
+        if (s->used == s->ev.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            s->ev.push_back({a, b});
+        }
+        slot = s->used++;
+        cudaEventRecord(s->ev[slot].first, c->stream);
+    }
+    ~ProfScope() {
+        if (!c->prof) return;
+        cudaEventRecord(s->ev[slot].second, c->stream);
+    }
+};
+
+static void prof_collect(nav_ctx *c, ProfSlot *s) {
+    if (s->used == 0) return;
+    cudaStreamSynchronize(c->stream);
+    for (size_t i = 0; i < s->used; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, s->ev[i].first, s->ev[i].second) == cudaSuccess) s->ms += ms;
+        s->launches++;
+    }
+    s->used = 0;
+}
+
+extern "C" void nav_destroy(nav_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void *ptrs[] = {c->d_cloud, c->d_global, c->d_curv, c->d_nn_dist, c->d_labels, c->d_nn_idx, c->map.pts,
+                    c->map.col, c->map.rank, c->map.count, c->map.box, c->map.sbox, c->d_corr_rows, c->d_corr,
+                    c->d_corr_row_count, c->d_corr_total, c->d_dist, c->d_tan_col, c->d_tan_row, c->d_flat,
+                    c->d_flat_count};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (c->h_small) cudaFreeHost(c->h_small);
+    c->stage.release();
+    for (ProfSlot *s : {&c->prof_labels, &c->prof_match, &c->prof_map})
+        for (auto &e : s->ev) {
+            cudaEventDestroy(e.first);
+            cudaEventDestroy(e.second);
+        }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" nav_ctx *nav_create(int rows, int cols, int device, int n_seq) {
+    if (rows < 1 || cols < 1 || n_seq < 1 || n_seq > NAV_MAX_SEQ) {
+        fail("nav_create: bad shape %dx%d n_seq=%d (n_seq must be 1..%d)", rows, cols, n_seq, NAV_MAX_SEQ);
+        return nullptr;
+    }
+    int ndev = nav_device_count();
+    if (ndev == 0) {
+        fail("nav_create: no CUDA device visible -- libnavslam_b200 has no CPU fallback");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        fail("nav_create: device %d out of range (0..%d)", device, ndev - 1);
+        return nullptr;
+    }
+    CUP(cudaSetDevice(device));
+    nav_ctx *c = new nav_ctx();
+    c->rows = rows;
+    c->cols = cols;
+    c->n_seq = n_seq;
+    c->device = device;
+    c->npx = (size_t)rows * cols;
+    c->ntot = c->npx * n_seq;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (match_smem_bytes(cols, true) > (size_t)max_smem) {
+        fail("nav_create: %d columns need %zu B of shared memory per row CTA, device allows %d", cols,
+             match_smem_bytes(cols, true), max_smem);
+        delete c;
+        return nullptr;
+    }
+#define ALLOC(ptr, bytes)                                                             \
+    if (cudaMalloc((void **)&(ptr), (bytes)) != cudaSuccess) {                        \
+        fail("nav_create: cudaMalloc(%zu) failed for " #ptr, (size_t)(bytes));        \
+        nav_destroy(c);                                                               \
+        return nullptr;                                                               \
+    }
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail("nav_create: cudaStreamCreate failed");
+        delete c;
+        return nullptr;
+    }
+    c->stream = c->own_stream;
+    const size_t nt = c->ntot, nr = (size_t)n_seq * rows;
+    c->map.n_chunks = div_up(cols, kChunk);
+    c->map.n_super = div_up(c->map.n_chunks, kChunksPerSuper);
+    ALLOC(c->d_cloud, nt * 24);
+    ALLOC(c->d_global, nt * 24);
+    ALLOC(c->d_labels, nt * 4);
+    ALLOC(c->d_nn_idx, nt * 4);
+    ALLOC(c->d_nn_dist, nt * 8);
+    ALLOC(c->map.pts, nt * 24);
+    ALLOC(c->map.col, nt * 4);
+    ALLOC(c->map.rank, nt * 4);
+    ALLOC(c->map.count, nr * 4);
+    ALLOC(c->map.box, nr * c->map.n_chunks * 48);
+    ALLOC(c->map.sbox, nr * c->map.n_super * 48);
+    ALLOC(c->d_corr_rows, nt * sizeof(nav_corr));
+    ALLOC(c->d_corr, nt * sizeof(nav_corr));
+    ALLOC(c->d_corr_row_count, nr * 4);
+    ALLOC(c->d_corr_total, (size_t)n_seq * 4);
+    ALLOC(c->d_dist, c->npx * 4);
+    ALLOC(c->d_tan_col, (size_t)cols * 8);
+    ALLOC(c->d_tan_row, (size_t)rows * 8);
+    ALLOC(c->d_flat, (size_t)cols * 24 * 2 + (size_t)cols * 4);
+    ALLOC(c->d_flat_count, 4);
+#undef ALLOC
+    cudaMemsetAsync(c->map.count, 0, nr * 4, c->stream);
+    if (cudaHostAlloc((void **)&c->h_small, 4096, cudaHostAllocDefault) != cudaSuccess) {
+        fail("nav_create: pinned scratch allocation failed");
+        nav_destroy(c);
+        return nullptr;
+    }
+    // tan tables of utils/pointcloud.c:10-41, evaluated with the host libm exactly as the reference
+    {
+        std::vector<double> tc(cols), tr(rows);
+        const double fov = 45.0;
+        const double col_step = fov / (cols - 1), row_step = fov / (rows - 1);
+        for (int i = 0; i < cols; ++i) {
+            double theta = -fov / 2.0 + i * col_step;
+            theta = theta * M_PI / 180.0;
+            tc[i] = tan(theta);
+        }
+        for (int j = 0; j < rows; ++j) {
+            double phi = -fov / 2.0 + j * row_step;
+            phi = phi * M_PI / 180.0;
+            tr[j] = tan(phi);
+        }
+        cudaMemcpy(c->d_tan_col, tc.data(), (size_t)cols * 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(c->d_tan_row, tr.data(), (size_t)rows * 8, cudaMemcpyHostToDevice);
+    }
+    if (configure_row_kernels(cols) != 0) {
+        fail("nav_create: cannot opt in to %zu B dynamic shared memory", match_smem_bytes(cols, true));
+        nav_destroy(c);
+        return nullptr;
+    }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        fail("nav_create: device initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        nav_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+extern "C" int nav_rows(const nav_ctx *c) { return c ? c->rows : 0; }
+extern "C" int nav_cols(const nav_ctx *c) { return c ? c->cols : 0; }
+extern "C" uint64_t nav_launch_count(const nav_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int nav_set_stream(nav_ctx *c, void *s) {
+    if (!c) return fail("nav_set_stream: null context");
+    CU(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+
+extern "C" int nav_synchronize(nav_ctx *c) {
+    if (!c) return fail("nav_synchronize: null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int nav_profile_enable(nav_ctx *c, int on) {
+    if (!c) return fail("nav_profile_enable: null context");
+    c->prof = on != 0;
+    return 0;
+}
+
+extern "C" int nav_profile_read(nav_ctx *c, const char *name, double *ms, uint64_t *launches, int reset) {
+    if (!c || !name) return fail("nav_profile_read: null argument");
+    ProfSlot *s = !strcmp(name, "labels") ? &c->prof_labels
+                  : !strcmp(name, "match") ? &c->prof_match
+                  : !strcmp(name, "map")   ? &c->prof_map
+                                           : nullptr;
+    if (!s) return fail("nav_profile_read: unknown kernel '%s'", name);
+    prof_collect(c, s);
+    if (ms) *ms = s->ms;
+    if (launches) *launches = s->launches;
+    if (reset) {
+        s->ms = 0;
+        s->launches = 0;
+    }
+    return 0;
+}
+
+#define CTX_ENTER(c, name)                                  \
+    if (!(c)) return fail(name ": null context");           \
+    CU(cudaSetDevice((c)->device));
+
+static int finish_call(nav_ctx *c, const char *name) {
+    if (c->stage.finish(c->stream)) {
+        cudaError_t e = cudaGetLastError();
+        return fail("%s: device execution failed: %s", name, cudaGetErrorString(e));
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("%s: %s", name, cudaGetErrorString(e));
+    return 0;
+}
+
+// device-side building blocks (no sync) -------------------------------------------------------
+static void run_labels(nav_ctx *c, const double *d_cloud, int *d_labels, double *d_curv, size_t n_images) {
+    ProfScope ps(c, &c->prof_labels);
+    launch_labels(d_cloud, d_labels, d_curv, (long long)n_images * c->rows, c->cols, c->sm_count, c->stream);
+    c->launches++;
+}
+
+static void run_map(nav_ctx *c, const double *d_cloud, const PoseBatch &poses, bool write_global) {
+    ProfScope ps(c, &c->prof_map);
+    launch_map_build(d_cloud, c->d_labels, write_global ? c->d_global : nullptr, c->map, poses, c->n_seq,
+                     c->rows, c->cols, c->stream);
+    c->launches++;
+    c->have_map = true;
+}
+
+static void run_match(nav_ctx *c, const double *d_cloud, const PoseBatch &poses, bool dedupe) {
+    MatchOut out = {c->d_nn_idx, c->d_nn_dist, c->d_corr_rows, c->d_corr_row_count};
+    {
+        ProfScope ps(c, &c->prof_match);
+        launch_match(d_cloud, c->d_labels, c->map, out, poses, c->n_seq, c->rows, c->cols, dedupe, c->stream);
+        c->launches++;
+    }
+    if (dedupe) {
+        launch_gather_corr(c->d_corr_rows, c->d_corr_row_count, c->d_corr, c->d_corr_total, c->n_seq, c->rows,
+                           c->cols, c->stream);
+        c->launches++;
+    }
+}
+
+static PoseBatch pose_batch(const nav_ctx *c, const nav_pos *pos, const nav_pos *last) {
+    PoseBatch b;
+    memset(&b, 0, sizeof(b));
+    for (int s = 0; s < c->n_seq; ++s) b.p[s] = make_pose(&pos[s], last ? &last[s] : nullptr);
+    return b;
+}
+
+// ------------------------------------------------------------------ function level ----------
+extern "C" int nav_convert_to_pointcloud(nav_ctx *c, const int *distances, nav_point *cloud_out) {
+    CTX_ENTER(c, "nav_convert_to_pointcloud");
+    if (!distances || !cloud_out) return fail("nav_convert_to_pointcloud: null argument");
+    if (c->stage.reserve(c->npx * 28 + 512, c->stream)) return fail("nav_convert_to_pointcloud: staging");
+    if (c->stage.h2d(c->d_dist, distances, c->npx * 4, c->stream)) return fail("nav_convert_to_pointcloud: H2D");
+    launch_convert(c->d_dist, c->d_tan_col, c->d_tan_row, c->d_cloud, c->rows, c->cols, c->sm_count, c->stream);
+    c->launches++;
+    c->cloud_resident = false;
+    if (c->stage.d2h(cloud_out, c->d_cloud, c->npx * 24, c->stream)) return fail("nav_convert_to_pointcloud: D2H");
+    return finish_call(c, "nav_convert_to_pointcloud");
+}
+
+extern "C" int nav_extract_feature(nav_ctx *c, const nav_point *cloud, int *feature) {
+    CTX_ENTER(c, "nav_extract_feature");
+    if (!cloud || !feature) return fail("nav_extract_feature: null argument");
+    if (c->stage.reserve(c->npx * 28 + 512, c->stream)) return fail("nav_extract_feature: staging");
+    if (c->stage.h2d(c->d_cloud, cloud, c->npx * 24, c->stream)) return fail("nav_extract_feature: H2D");
+    c->cloud_resident = false;
+    run_labels(c, c->d_cloud, c->d_labels, nullptr, 1);
+    int *lab = (int *)c->stage.take(c->npx * 4, c->stream);
+    if (!lab) return fail("nav_extract_feature: staging");
+    CU(cudaMemcpyAsync(lab, c->d_labels, c->npx * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (finish_call(c, "nav_extract_feature")) return 1;
+    // the reference only ever stores 1s (src/slam.c:58); whatever the caller had elsewhere stays
+    for (size_t i = 0; i < c->npx; ++i)
+        if (lab[i]) feature[i] = 1;
+    return 0;
+}
+
+extern "C" int nav_curvature(nav_ctx *c, const nav_point *cloud, double *curv_out) {
+    CTX_ENTER(c, "nav_curvature");
+    if (!cloud || !curv_out) return fail("nav_curvature: null argument");
+    if (!c->d_curv) CU(cudaMalloc((void **)&c->d_curv, c->npx * 8));
+    if (c->stage.reserve(c->npx * 32 + 512, c->stream)) return fail("nav_curvature: staging");
+    if (c->stage.h2d(c->d_cloud, cloud, c->npx * 24, c->stream)) return fail("nav_curvature: H2D");
+    c->cloud_resident = false;
+    run_labels(c, c->d_cloud, c->d_labels, c->d_curv, 1);
+    if (c->stage.d2h(curv_out, c->d_curv, c->npx * 8, c->stream)) return fail("nav_curvature: D2H");
+    return finish_call(c, "nav_curvature");
+}
+
+extern "C" int nav_flatten_points(nav_ctx *c, const nav_point *row_points, const int *row_feature,
+                                  nav_point *flattened_out, size_t *num_points_out) {
+    CTX_ENTER(c, "nav_flatten_points");
+    if (!row_points || !row_feature || !flattened_out || !num_points_out)
+        return fail("nav_flatten_points: null argument");
+    const size_t cols = c->cols;
+    double *d_in = c->d_flat, *d_out = c->d_flat + cols * 3;
+    int *d_feat = (int *)(c->d_flat + cols * 6);
+    if (c->stage.reserve(cols * 56 + 1024, c->stream)) return fail("nav_flatten_points: staging");
+    if (c->stage.h2d(d_in, row_points, cols * 24, c->stream)) return fail("nav_flatten_points: H2D");
+    if (c->stage.h2d(d_feat, row_feature, cols * 4, c->stream)) return fail("nav_flatten_points: H2D");
+    launch_flatten_row(d_in, d_feat, d_out, c->d_flat_count, c->cols, c->stream);
+    c->launches++;
+    CU(cudaMemcpyAsync(c->h_small, c->d_flat_count, 4, cudaMemcpyDeviceToHost, c->stream));
+    unsigned char *tmp = c->stage.take(cols * 24, c->stream);
+    if (!tmp) return fail("nav_flatten_points: staging");
+    CU(cudaMemcpyAsync(tmp, d_out, cols * 24, cudaMemcpyDeviceToHost, c->stream));
+    if (finish_call(c, "nav_flatten_points")) return 1;
+    const size_t n = (size_t)c->h_small[0];
+    memcpy(flattened_out, tmp, n * 24);  // like the reference, entries past n are left untouched
+    *num_points_out = n;
+    return 0;
+}
+
+extern "C" int nav_transform_cloud(nav_ctx *c, const nav_point *cloud, const nav_pos *pos, nav_point *global_out) {
+    CTX_ENTER(c, "nav_transform_cloud");
+    if (!cloud || !pos || !global_out) return fail("nav_transform_cloud: null argument");
+    if (c->stage.reserve(c->npx * 48 + 512, c->stream)) return fail("nav_transform_cloud: staging");
+    if (c->stage.h2d(c->d_cloud, cloud, c->npx * 24, c->stream)) return fail("nav_transform_cloud: H2D");
+    c->cloud_resident = false;
+    launch_transform(c->d_cloud, c->d_global, (long long)c->npx, make_pose(pos, nullptr), c->sm_count, c->stream);
+    c->launches++;
+    if (c->stage.d2h(global_out, c->d_global, c->npx * 24, c->stream)) return fail("nav_transform_cloud: D2H");
+    return finish_call(c, "nav_transform_cloud");
+}
+
+// ------------------------------------------------------------------ SLAM step ----------------
+static int upload_cloud(nav_ctx *c, const nav_point *cloud, const char *name) {
+    if (c->stage.h2d(c->d_cloud, cloud, c->ntot * 24, c->stream)) return fail("%s: H2D of the cloud failed", name);
+    return 0;
+}
+
+extern "C" int nav_slam_init(nav_ctx *c, const nav_pos *pos, const nav_point *cloud, nav_point *global_out) {
+    CTX_ENTER(c, "nav_slam_init");
+    if (!pos || !cloud) return fail("nav_slam_init: null argument");
+    if (c->stage.reserve(c->ntot * 48 + 1024, c->stream)) return fail("nav_slam_init: staging");
+    if (upload_cloud(c, cloud, "nav_slam_init")) return 1;
+    run_labels(c, c->d_cloud, c->d_labels, nullptr, c->n_seq);
+    run_map(c, c->d_cloud, pose_batch(c, pos, nullptr), true);
+    c->cloud_resident = true;
+    if (global_out && c->stage.d2h(global_out, c->d_global, c->ntot * 24, c->stream))
+        return fail("nav_slam_init: D2H");
+    return finish_call(c, "nav_slam_init");
+}
+
+extern "C" int nav_slam_init_dev(nav_ctx *c, const void *dev_cloud, const nav_pos *pos) {
+    CTX_ENTER(c, "nav_slam_init_dev");
+    if (!pos || !dev_cloud) return fail("nav_slam_init_dev: null argument");
+    run_labels(c, (const double *)dev_cloud, c->d_labels, nullptr, c->n_seq);
+    run_map(c, (const double *)dev_cloud, pose_batch(c, pos, nullptr), true);
+    c->cloud_resident = false;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nav_slam_match(nav_ctx *c, const nav_point *cloud, const nav_pos *pos_predict,
+                              const nav_pos *pos_last, nav_corr *corr_out, size_t corr_cap, size_t *n_corr_out) {
+    CTX_ENTER(c, "nav_slam_match");
+    if (!cloud || !pos_predict || !pos_last || !n_corr_out) return fail("nav_slam_match: null argument");
+    if (c->n_seq != 1) return fail("nav_slam_match: host correspondence lists need n_seq == 1");
+    if (!c->have_map) return fail("nav_slam_match: call nav_slam_init first");
+    if (c->stage.reserve(c->ntot * 24 + c->ntot * sizeof(nav_corr) + 1024, c->stream))
+        return fail("nav_slam_match: staging");
+    if (upload_cloud(c, cloud, "nav_slam_match")) return 1;
+    run_labels(c, c->d_cloud, c->d_labels, nullptr, c->n_seq);
+    run_match(c, c->d_cloud, pose_batch(c, pos_predict, pos_last), true);
+    c->cloud_resident = true;
+    CU(cudaMemcpyAsync(c->h_small, c->d_corr_total, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const size_t n = (size_t)c->h_small[0];
+    *n_corr_out = n;
+    const size_t take = n < corr_cap ? n : corr_cap;
+    if (corr_out && take && c->stage.d2h(corr_out, c->d_corr, take * sizeof(nav_corr), c->stream))
+        return fail("nav_slam_match: D2H");
+    return finish_call(c, "nav_slam_match");
+}
+
+// the reference's translation-only Adam fit, src/slam.c:218-379, on the deduped correspondences.
+// Sequential binary64 sums in list order: bit-identical to the reference by construction.
+static void adam_fit(const nav_corr *res, size_t count, double transform[6], double *error_out, int verbose) {
+    const double lr = 0.1, tol = 1e-6, b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    double m[3] = {0, 0, 0}, v[3] = {0, 0, 0};
+    double prev = 0, total = 0;
+    int valid = 0;
+    for (int iter = 0; iter < 200; ++iter) {
+        double g[3] = {0.0, 0.0, 0.0};
+        total = 0;
+        valid = 0;
+        for (size_t i = 0; i < count; ++i) {
+            const double dx = (res[i].ori.x - transform[0]) - res[i].nearest.x;
+            const double dy = (res[i].ori.y - transform[1]) - res[i].nearest.y;
+            const double dz = (res[i].ori.z - transform[2]) - res[i].nearest.z;
+            total += dx * dx + dy * dy + dz * dz;
+            g[0] -= dx;
+            g[1] -= dy;
+            g[2] -= dz;
+            ++valid;
+        }
+        if (fabs(total - prev) < tol) {
+            if (verbose) printf("收敛，停止迭代！\n");
+            break;
+        }
+        prev = total;
+        if (valid > 0) {
+            g[0] /= valid;
+            g[1] /= valid;
+            g[2] /= valid;
+        }
+        const int t = iter + 1;
+        for (int j = 0; j < 3; ++j) {
+            m[j] = b1 * m[j] + (1 - b1) * g[j];
+            v[j] = b2 * v[j] + (1 - b2) * g[j] * g[j];
+            const double mh = m[j] / (1 - pow(b1, t));
+            const double vh = v[j] / (1 - pow(b2, t));
+            transform[j] -= lr * mh / (sqrt(vh) + eps);
+        }
+        if (verbose) printf("Iteration %d, Total Error: %.6f\n", iter, total);
+    }
+    *error_out = valid > 0 ? sqrt(total / valid) : 0.0;
+}
+
+extern "C" int nav_slam_localization(nav_ctx *c, const nav_point *cloud, const nav_pos *pos_predict,
+                                     const nav_pos *pos_last, nav_pos *pos_out, double *error_out, int verbose) {
+    CTX_ENTER(c, "nav_slam_localization");
+    if (!pos_out) return fail("nav_slam_localization: null argument");
+    static thread_local std::vector<nav_corr> corr;
+    corr.resize(c->npx);
+    size_t n = 0;
+    if (nav_slam_match(c, cloud, pos_predict, pos_last, corr.data(), corr.size(), &n)) return 1;
+    double transform[6] = {pos_predict->x - pos_last->x,       pos_predict->y - pos_last->y,
+                           pos_predict->z - pos_last->z,       pos_predict->roll - pos_last->roll,
+                           pos_predict->pitch - pos_last->pitch, pos_predict->yaw - pos_last->yaw};
+    double err = 0.0;
+    adam_fit(corr.data(), n, transform, &err, verbose);
+    if (error_out) *error_out = err;
+    pos_out->x = pos_last->x + transform[0];
+    pos_out->y = pos_last->y + transform[1];
+    pos_out->z = pos_last->z + transform[2];
+    pos_out->roll = pos_last->roll + transform[3];
+    pos_out->pitch = pos_last->pitch + transform[4];
+    pos_out->yaw = pos_last->yaw + transform[5];
+    return 0;
+}
+
+extern "C" int nav_slam_mapping(nav_ctx *c, const nav_pos *pos, const nav_point *cloud, nav_point *global_out) {
+    CTX_ENTER(c, "nav_slam_mapping");
+    if (!pos) return fail("nav_slam_mapping: null argument");
+    if (c->stage.reserve(c->ntot * 48 + 1024, c->stream)) return fail("nav_slam_mapping: staging");
+    if (cloud) {
+        if (upload_cloud(c, cloud, "nav_slam_mapping")) return 1;
+        run_labels(c, c->d_cloud, c->d_labels, nullptr, c->n_seq);
+        c->cloud_resident = true;
+    } else if (!c->cloud_resident) {
+        return fail("nav_slam_mapping: cloud == NULL but no cloud is resident from a preceding match");
+    }
+    run_map(c, c->d_cloud, pose_batch(c, pos, nullptr), true);
+    if (global_out && c->stage.d2h(global_out, c->d_global, c->ntot * 24, c->stream))
+        return fail("nav_slam_mapping: D2H");
+    return finish_call(c, "nav_slam_mapping");
+}
+
+extern "C" int nav_frontend_frame(nav_ctx *c, const nav_point *cloud, const nav_pos *pos_predict,
+                                  const nav_pos *pos_last, const nav_pos *pos_final, int *feature_out,
+                                  int32_t *nn_idx_out, double *nn_dist_out, nav_point *global_out) {
+    CTX_ENTER(c, "nav_frontend_frame");
+    if (!cloud || !pos_predict || !pos_last || !pos_final) return fail("nav_frontend_frame: null argument");
+    if (!c->have_map) return fail("nav_frontend_frame: call nav_slam_init first");
+    if (c->stage.reserve(c->ntot * (24 + 24 + 4 + 4 + 8) + 4096, c->stream)) return fail("nav_frontend_frame: staging");
+    if (upload_cloud(c, cloud, "nav_frontend_frame")) return 1;
+    run_labels(c, c->d_cloud, c->d_labels, nullptr, c->n_seq);
+    run_match(c, c->d_cloud, pose_batch(c, pos_predict, pos_last), false);
+    run_map(c, c->d_cloud, pose_batch(c, pos_final, nullptr), true);
+    c->cloud_resident = true;
+    if (feature_out && c->stage.d2h(feature_out, c->d_labels, c->ntot * 4, c->stream)) return fail("nav_frontend_frame: D2H");
+    if (nn_idx_out && c->stage.d2h(nn_idx_out, c->d_nn_idx, c->ntot * 4, c->stream)) return fail("nav_frontend_frame: D2H");
+    if (nn_dist_out && c->stage.d2h(nn_dist_out, c->d_nn_dist, c->ntot * 8, c->stream)) return fail("nav_frontend_frame: D2H");
+    if (global_out && c->stage.d2h(global_out, c->d_global, c->ntot * 24, c->stream)) return fail("nav_frontend_frame: D2H");
+    return finish_call(c, "nav_frontend_frame");
+}
+
+// ------------------------------------------------------------------ device resident ----------
+extern "C" int nav_extract_feature_batch_dev(nav_ctx *c, const void *dev_clouds, size_t n_images, void *dev_labels) {
+    CTX_ENTER(c, "nav_extract_feature_batch_dev");
+    if (!dev_clouds || !dev_labels) return fail("nav_extract_feature_batch_dev: null argument");
+    run_labels(c, (const double *)dev_clouds, (int *)dev_labels, nullptr, n_images);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nav_frontend_frame_dev(nav_ctx *c, const void *dev_cloud, const nav_pos *pos_predict,
+                                      const nav_pos *pos_last, const nav_pos *pos_final) {
+    CTX_ENTER(c, "nav_frontend_frame_dev");
+    if (!dev_cloud || !pos_predict || !pos_last || !pos_final) return fail("nav_frontend_frame_dev: null argument");
+    if (!c->have_map) return fail("nav_frontend_frame_dev: call nav_slam_init_dev first");
+    const double *cl = (const double *)dev_cloud;
+    run_labels(c, cl, c->d_labels, nullptr, c->n_seq);
+    run_match(c, cl, pose_batch(c, pos_predict, pos_last), false);
+    run_map(c, cl, pose_batch(c, pos_final, nullptr), true);
+    c->cloud_resident = false;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nav_frame_results_dev(nav_ctx *c, nav_frame_results *out) {
+    if (!c || !out) return fail("nav_frame_results_dev: null argument");
+    out->labels = c->d_labels;
+    out->nn_idx = c->d_nn_idx;
+    out->nn_dist = c->d_nn_dist;
+    out->global = c->d_global;
+    out->map_count = c->map.count;
+    return 0;
+}
+
+extern "C" int nav_row_map_export(nav_ctx *c, int seq, int row, nav_point *pts_out, int32_t *col_out, size_t *n_out) {
+    CTX_ENTER(c, "nav_row_map_export");
+    if (!pts_out || !n_out) return fail("nav_row_map_export: null argument");
+    if (seq < 0 || seq >= c->n_seq || row < 0 || row >= c->rows) return fail("nav_row_map_export: bad row");
+    CU(cudaStreamSynchronize(c->stream));
+    const size_t rid = (size_t)seq * c->rows + row;
+    int n = 0;
+    if (c->have_map) CU(cudaMemcpy(&n, c->map.count + rid, 4, cudaMemcpyDeviceToHost));
+    if (n > 0) {
+        CU(cudaMemcpy(pts_out, c->map.pts + rid * c->cols * 3, (size_t)n * 24, cudaMemcpyDeviceToHost));
+        if (col_out) CU(cudaMemcpy(col_out, c->map.col + rid * c->cols, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    }
+    *n_out = (size_t)n;
+    return 0;
+}
+
+// ------------------------------------------------------------------ kd-tree ------------------
+struct nav_kdtree {
+    int device = 0, sm_count = 148;
+    size_t n = 0;
+    KdNode *d_nodes = nullptr;
+    double *d_pts = nullptr;  // build input order, for nearest_out
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    // query scratch
+    double *d_q = nullptr, *d_dist = nullptr;
+    int *d_idx = nullptr;
+    size_t q_cap = 0;
+};
+
+extern "C" void nav_kdtree_free(nav_kdtree *t) {
+    if (!t) return;
+    cudaSetDevice(t->device);
+    if (t->stream) cudaStreamSynchronize(t->stream);
+    for (void *p : {(void *)t->d_nodes, (void *)t->d_pts, (void *)t->d_q, (void *)t->d_dist, (void *)t->d_idx})
+        if (p) cudaFree(p);
+    if (t->stream) cudaStreamDestroy(t->stream);
+    delete t;
+}
+
+static nav_kdtree *kd_new(int device, size_t n) {
+    int ndev = nav_device_count();
+    if (ndev == 0) {
+        fail("nav_kdtree_build: no CUDA device visible -- libnavslam_b200 has no CPU fallback");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        fail("nav_kdtree_build: device %d out of range", device);
+        return nullptr;
+    }
+    if (n > (size_t)0x7fffffff) {
+        fail("nav_kdtree_build: %zu points exceed the 2^31-1 limit of int32 indices", n);
+        return nullptr;
+    }
+    CUP(cudaSetDevice(device));
+    nav_kdtree *t = new nav_kdtree();
+    t->device = device;
+    t->n = n;
+    cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        (n && (cudaMalloc((void **)&t->d_nodes, n * sizeof(KdNode)) != cudaSuccess ||
+               cudaMalloc((void **)&t->d_pts, n * 24) != cudaSuccess))) {
+        fail("nav_kdtree_build: device allocation for %zu points failed", n);
+        nav_kdtree_free(t);
+        return nullptr;
+    }
+    return t;
+}
+
+extern "C" nav_kdtree *nav_kdtree_build_dev(int device, const void *dev_points, size_t n, void *cuda_stream) {
+    if (n && !dev_points) {
+        fail("nav_kdtree_build_dev: null points");
+        return nullptr;
+    }
+    nav_kdtree *t = kd_new(device, n);
+    if (!t) return nullptr;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : t->stream;
+    cudaError_t e = cudaSuccess;
+    if (n) {
+        e = cudaMemcpyAsync(t->d_pts, dev_points, n * 24, cudaMemcpyDeviceToDevice, s);
+        if (e == cudaSuccess) e = kd_build(t->d_pts, n, t->d_nodes, t->sm_count, s, &t->launches);
+    }
+    if (e != cudaSuccess) {
+        fail("nav_kdtree_build_dev: %s", cudaGetErrorString(e));
+        nav_kdtree_free(t);
+        return nullptr;
+    }
+    return t;
+}
+
+extern "C" nav_kdtree *nav_kdtree_build(int device, const nav_point *points, size_t n) {
+    if (n && !points) {
+        fail("nav_kdtree_build: null points");
+        return nullptr;
+    }
+    nav_kdtree *t = kd_new(device, n);
+    if (!t) return nullptr;
+    cudaError_t e = cudaSuccess;
+    if (n) {
+        e = cudaMemcpyAsync(t->d_pts, points, n * 24, cudaMemcpyHostToDevice, t->stream);
+        if (e == cudaSuccess) e = kd_build(t->d_pts, n, t->d_nodes, t->sm_count, t->stream, &t->launches);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
+    }
+    if (e != cudaSuccess) {
+        fail("nav_kdtree_build: %s", cudaGetErrorString(e));
+        nav_kdtree_free(t);
+        return nullptr;
+    }
+    return t;
+}
+
+extern "C" size_t nav_kdtree_size(const nav_kdtree *t) { return t ? t->n : 0; }
+extern "C" uint64_t nav_kdtree_launch_count(const nav_kdtree *t) { return t ? t->launches : 0; }
+
+__global__ void k_gather_nearest(const double *__restrict__ pts, const int *__restrict__ idx, long long nq,
+                                 double *__restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nq;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int j = idx[i];
+        if (j >= 0) {
+            out[i * 3] = pts[(long long)j * 3];
+            out[i * 3 + 1] = pts[(long long)j * 3 + 1];
+            out[i * 3 + 2] = pts[(long long)j * 3 + 2];
+        }
+    }
+}
+
+extern "C" int nav_kdtree_nn_batch_dev(nav_kdtree *t, const void *dev_queries, size_t nq, void *dev_idx,
+                                       void *dev_dist, void *cuda_stream) {
+    if (!t) return fail("nav_kdtree_nn_batch_dev: null tree");
+    if (nq && (!dev_queries || !dev_idx || !dev_dist)) return fail("nav_kdtree_nn_batch_dev: null argument");
+    CU(cudaSetDevice(t->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : t->stream;
+    CU(kd_nn(t->d_nodes, t->n, (const double *)dev_queries, nq, (int *)dev_idx, (double *)dev_dist, s, &t->launches));
+    return 0;
+}
+
+extern "C" int nav_kdtree_nn_batch(nav_kdtree *t, const nav_point *queries, size_t nq, int32_t *idx_out,
+                                   double *dist_out, nav_point *nearest_out) {
+    if (!t) return fail("nav_kdtree_nn_batch: null tree");
+    if (nq == 0) return 0;
+    if (!queries || !idx_out || !dist_out) return fail("nav_kdtree_nn_batch: null argument");
+    CU(cudaSetDevice(t->device));
+    if (nq > t->q_cap) {
+        for (void *p : {(void *)t->d_q, (void *)t->d_dist, (void *)t->d_idx})
+            if (p) cudaFree(p);
+        t->d_q = t->d_dist = nullptr;
+        t->d_idx = nullptr;
+        t->q_cap = 0;
+        CU(cudaMalloc((void **)&t->d_q, nq * 24 * 2));  // queries + gathered nearest points
+        CU(cudaMalloc((void **)&t->d_dist, nq * 8));
+        CU(cudaMalloc((void **)&t->d_idx, nq * 4));
+        t->q_cap = nq;
+    }
+    CU(cudaMemcpyAsync(t->d_q, queries, nq * 24, cudaMemcpyHostToDevice, t->stream));
+    CU(kd_nn(t->d_nodes, t->n, t->d_q, nq, t->d_idx, t->d_dist, t->stream, &t->launches));
+    CU(cudaMemcpyAsync(idx_out, t->d_idx, nq * 4, cudaMemcpyDeviceToHost, t->stream));
+    CU(cudaMemcpyAsync(dist_out, t->d_dist, nq * 8, cudaMemcpyDeviceToHost, t->stream));
+    if (nearest_out && t->n) {
+        double *d_near = t->d_q + nq * 3;
+        k_gather_nearest<<<(unsigned)((nq + 255) / 256), 256, 0, t->stream>>>(t->d_pts, t->d_idx, (long long)nq, d_near);
+        t->launches++;
+        CU(cudaMemcpyAsync(nearest_out, d_near, nq * 24, cudaMemcpyDeviceToHost, t->stream));
+    }
+    CU(cudaStreamSynchronize(t->stream));
+    return 0;
+}
+
+extern "C" int nav_kdtree_export(nav_kdtree *t, nav_point *nodes_out, int32_t *orig_idx_out) {
+    if (!t || !nodes_out || !orig_idx_out) return fail("nav_kdtree_export: null argument");
+    CU(cudaSetDevice(t->device));
+    std::vector<KdNode> h(t->n);
+    CU(cudaMemcpy(h.data(), t->d_nodes, t->n * sizeof(KdNode), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < t->n; ++i) {
+        nodes_out[i].x = h[i].x;
+        nodes_out[i].y = h[i].y;
+        nodes_out[i].z = h[i].z;
+        orig_idx_out[i] = h[i].idx;
+    }
+    return 0;
+}
+
+extern "C" int nav_bruteforce_nn_batch_dev(int device, const void *dev_points, size_t n, const void *dev_queries,
+                                           size_t nq, void *dev_idx, void *dev_dist, int use_tensor_cores,
+                                           void *cuda_stream) {
+    if (nav_device_count() == 0) return fail("nav_bruteforce_nn_batch_dev: no CUDA device");
+    if (nq && (!dev_queries || !dev_idx || !dev_dist || (n && !dev_points)))
+        return fail("nav_bruteforce_nn_batch_dev: null argument");
+    if (use_tensor_cores)
+        return fail("nav_bruteforce_nn_batch_dev: the tensor-core candidate path is not built in this version");
+    CU(cudaSetDevice(device));
+    CU(bf_nn((const double *)dev_points, n, (const double *)dev_queries, nq, (int *)dev_idx, (double *)dev_dist,
+             (cudaStream_t)cuda_stream));
+    return 0;
+}

@@ -1,0 +1,382 @@
+// kdtree.cu -- flat implicit kd-tree for large maps (a5) and batched exact 1-NN (a6).
+//
+// Reference: utils/kdtree.c:65-82 builds a pointer tree by recursive median split (axis =
+// depth % 3, median index n/2, children on [0,m) and [m+1,n)) with one malloc per node and an
+// in-place Lomuto quick-select; utils/kdtree.c:110-152 answers one query per call by recursion.
+//
+// Here the tree is the *in-order array* that recursion leaves behind: the node of range [lo,hi)
+// sits at mid = lo + (hi-lo)/2, its children own [lo,mid) and [mid+1,hi) -- the same shape rule
+// as the reference, so with distinct keys it is the same tree.  Nodes are 32-byte records
+// {x,y,z,orig_index} (one DRAM sector each, subtrees contiguous in memory).
+//
+// Build, level by level, all segments of a level at once (no recursion, no per-node allocation):
+//   1. three index lists, each sorted along one axis (radix sort of order-preserving 64-bit keys);
+//   2. at level L the list of axis L%3 already holds every segment sorted, so the median of
+//      every segment is simply its middle element: mark each point left / median / right;
+//   3. the two other lists are stably partitioned inside every segment (one prefix sum of packed
+//      left/median counts + one scatter), which keeps them sorted for the levels below.
+// After ceil(log2 n) levels the three lists coincide and are the in-order layout.
+//
+// Query: one thread per query, stackless.  Child ranges are pure arithmetic on (lo,hi); the way
+// back up is recovered from two bit masks (which side was taken, parity of each ancestor's size),
+// so the traversal keeps no stack and re-reads only the split coordinate of an ancestor (L1/L2
+// hits).  Far subtrees are visited iff the rounded plane distance^2 is <= the current best dsq;
+// candidates compare lexicographically on (dsq, original index): exact NN, lowest index on ties.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <math.h>
+
+#include "nav_kdtree.cuh"
+
+namespace nav {
+
+// ------------------------------------------------------------------------------ build ------
+__device__ __forceinline__ unsigned long long order_key(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void k_make_keys(const double *__restrict__ pts, long long n, unsigned long long *__restrict__ kx,
+                            unsigned long long *__restrict__ ky, unsigned long long *__restrict__ kz,
+                            int *__restrict__ idx) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        kx[i] = order_key(pts[i * 3]);
+        ky[i] = order_key(pts[i * 3 + 1]);
+        kz[i] = order_key(pts[i * 3 + 2]);
+        idx[i] = (int)i;
+    }
+}
+
+// segment of position p at `level`: descend from the root range by arithmetic.
+// returns false if p became a node at a shallower level.
+__device__ __forceinline__ bool segment_of(int p, int n, int level, int &lo, int &hi) {
+    lo = 0;
+    hi = n;
+    for (int l = 0; l < level; ++l) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (p < mid)
+            hi = mid;
+        else if (p == mid)
+            return false;
+        else
+            lo = mid + 1;
+    }
+    return true;
+}
+
+// side codes: 0 left, 1 median (becomes the node), 2 right
+__global__ void k_mark(const int *__restrict__ listA, int n, int level, int *__restrict__ seg_lo,
+                       int *__restrict__ seg_mid, unsigned char *__restrict__ side) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        int lo, hi;
+        if (!segment_of(p, n, level, lo, hi)) {
+            seg_lo[p] = -1;
+            seg_mid[p] = -1;
+            continue;
+        }
+        const int mid = lo + ((hi - lo) >> 1);
+        seg_lo[p] = lo;
+        seg_mid[p] = mid;
+        side[listA[p]] = p < mid ? 0 : (p == mid ? 1 : 2);
+    }
+}
+
+__global__ void k_flags(const int *__restrict__ listX, int n, const int *__restrict__ seg_lo,
+                        const unsigned char *__restrict__ side, unsigned long long *__restrict__ flags) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        unsigned long long f = 0;
+        if (seg_lo[p] >= 0) {
+            const unsigned char s = side[listX[p]];
+            f = s == 0 ? 1ull : (s == 1 ? (1ull << 32) : 0ull);
+        }
+        flags[p] = f;
+    }
+}
+
+__global__ void k_scatter(const int *__restrict__ listX, int *__restrict__ listOut, int n,
+                          const int *__restrict__ seg_lo, const int *__restrict__ seg_mid,
+                          const unsigned char *__restrict__ side, const unsigned long long *__restrict__ scan) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const int idx = listX[p];
+        const int lo = seg_lo[p];
+        if (lo < 0) {
+            listOut[p] = idx;
+            continue;
+        }
+        const int mid = seg_mid[p];
+        const unsigned long long rel = scan[p] - scan[lo];
+        const int lefts = (int)(rel & 0xffffffffull), meds = (int)(rel >> 32);
+        const unsigned char s = side[idx];
+        int dst;
+        if (s == 0)
+            dst = lo + lefts;
+        else if (s == 1)
+            dst = mid;
+        else
+            dst = mid + 1 + ((p - lo) - lefts - meds);
+        listOut[dst] = idx;
+    }
+}
+
+__global__ void k_emit_nodes(const double *__restrict__ pts, const int *__restrict__ order, int n,
+                             KdNode *__restrict__ nodes) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const int i = order[p];
+        KdNode nd;
+        nd.x = pts[(long long)i * 3];
+        nd.y = pts[(long long)i * 3 + 1];
+        nd.z = pts[(long long)i * 3 + 2];
+        nd.idx = i;
+        nd.pad = 0;
+        nodes[p] = nd;
+    }
+}
+
+#define KD_CHECK(call)                     \
+    do {                                   \
+        cudaError_t e_ = (call);           \
+        if (e_ != cudaSuccess) {           \
+            status = e_;                   \
+            goto done;                     \
+        }                                  \
+    } while (0)
+
+cudaError_t kd_build(const double *d_pts, size_t n_sz, KdNode *d_nodes, int sm_count, cudaStream_t stream,
+                     uint64_t *launches) {
+    if (n_sz == 0) return cudaSuccess;
+    if (n_sz > (size_t)0x7fffffff) return cudaErrorInvalidValue;
+    const int n = (int)n_sz;
+    cudaError_t status = cudaSuccess;
+    unsigned long long *keys = nullptr, *keys_alt = nullptr, *flags = nullptr;
+    int *idx0 = nullptr, *lists = nullptr, *lists_alt = nullptr, *seg_lo = nullptr, *seg_mid = nullptr;
+    unsigned char *side = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_sort = 0, tmp_scan = 0, tmp_bytes = 0;
+    uint64_t nl = 0;
+    const int threads = 256;
+    int grid = (int)((n_sz + threads - 1) / threads);
+    if (grid > sm_count * 16) grid = sm_count * 16;
+
+    KD_CHECK(cudaMallocAsync(&keys, sizeof(unsigned long long) * n_sz * 3, stream));
+    KD_CHECK(cudaMallocAsync(&keys_alt, sizeof(unsigned long long) * n_sz, stream));
+    KD_CHECK(cudaMallocAsync(&flags, sizeof(unsigned long long) * n_sz, stream));
+    KD_CHECK(cudaMallocAsync(&idx0, sizeof(int) * n_sz, stream));
+    KD_CHECK(cudaMallocAsync(&lists, sizeof(int) * n_sz * 3, stream));
+    KD_CHECK(cudaMallocAsync(&lists_alt, sizeof(int) * n_sz * 3, stream));
+    KD_CHECK(cudaMallocAsync(&seg_lo, sizeof(int) * n_sz, stream));
+    KD_CHECK(cudaMallocAsync(&seg_mid, sizeof(int) * n_sz, stream));
+    KD_CHECK(cudaMallocAsync(&side, n_sz, stream));
+    KD_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys, keys_alt, idx0, lists, n, 0, 64, stream));
+    KD_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, flags, flags, n, stream));
+    tmp_bytes = tmp_sort > tmp_scan ? tmp_sort : tmp_scan;
+    KD_CHECK(cudaMallocAsync(&tmp, tmp_bytes, stream));
+
+    k_make_keys<<<grid, threads, 0, stream>>>(d_pts, n, keys, keys + n_sz, keys + 2 * n_sz, idx0);
+    ++nl;
+    for (int a = 0; a < 3; ++a) {
+        KD_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_sort, keys + a * n_sz, keys_alt, idx0,
+                                                 lists + a * n_sz, n, 0, 64, stream));
+        nl += 8;
+    }
+    {
+        int *cur = lists, *alt = lists_alt;
+        for (int level = 0; (n >> level) >= 2; ++level) {
+            const int a = level % 3, b = (a + 1) % 3, c = (a + 2) % 3;
+            k_mark<<<grid, threads, 0, stream>>>(cur + a * n_sz, n, level, seg_lo, seg_mid, side);
+            ++nl;
+            const int others[2] = {b, c};
+            for (int t = 0; t < 2; ++t) {
+                const int *src = cur + others[t] * n_sz;
+                int *dst = alt + others[t] * n_sz;
+                k_flags<<<grid, threads, 0, stream>>>(src, n, seg_lo, side, flags);
+                KD_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_scan, flags, flags, n, stream));
+                k_scatter<<<grid, threads, 0, stream>>>(src, dst, n, seg_lo, seg_mid, side, flags);
+                nl += 4;
+            }
+            // list a is already partitioned (it is sorted along the split axis): carry it over
+            KD_CHECK(cudaMemcpyAsync(alt + a * n_sz, cur + a * n_sz, sizeof(int) * n_sz,
+                                     cudaMemcpyDeviceToDevice, stream));
+            int *t2 = cur;
+            cur = alt;
+            alt = t2;
+        }
+        k_emit_nodes<<<grid, threads, 0, stream>>>(d_pts, cur, n, d_nodes);
+        ++nl;
+    }
+    KD_CHECK(cudaGetLastError());
+done:
+    cudaFreeAsync(keys, stream);
+    cudaFreeAsync(keys_alt, stream);
+    cudaFreeAsync(flags, stream);
+    cudaFreeAsync(idx0, stream);
+    cudaFreeAsync(lists, stream);
+    cudaFreeAsync(lists_alt, stream);
+    cudaFreeAsync(seg_lo, stream);
+    cudaFreeAsync(seg_mid, stream);
+    cudaFreeAsync(side, stream);
+    cudaFreeAsync(tmp, stream);
+    if (launches) *launches += nl;
+    return status;
+}
+
+// ------------------------------------------------------------------------------ query ------
+__device__ __forceinline__ void load_node(const KdNode *__restrict__ nodes, int i, double &x, double &y,
+                                          double &z, int &idx) {
+    const double2 *p = reinterpret_cast<const double2 *>(nodes + i);
+    const double2 a = __ldg(p);
+    const double2 b = __ldg(p + 1);
+    x = a.x;
+    y = a.y;
+    z = b.x;
+    idx = (int)(__double_as_longlong(b.y) & 0xffffffffll);
+}
+
+__device__ __forceinline__ double node_axis(const KdNode *__restrict__ nodes, int i, int axis) {
+    return __ldg(reinterpret_cast<const double *>(nodes + i) + axis);
+}
+
+__global__ void __launch_bounds__(128)
+k_kd_nn(const KdNode *__restrict__ nodes, int n, const double *__restrict__ queries, long long nq,
+        int *__restrict__ idx_out, double *__restrict__ dist_out) {
+    const long long qi = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    if (n <= 0) {  // utils/kdtree.c:112: NULL root leaves the outputs untouched; we report "none"
+        idx_out[qi] = -1;
+        dist_out[qi] = INFINITY;
+        return;
+    }
+    const double qx = queries[qi * 3], qy = queries[qi * 3 + 1], qz = queries[qi * 3 + 2];
+    double best = INFINITY;
+    int bidx = -1;
+
+    int lo = 0, hi = n, depth = 0;
+    unsigned path = 0, par = 0;  // bit d: side taken below the depth-d ancestor (1 = right) / its size parity
+    bool arriving_down = true;
+    while (true) {
+        const int mid = lo + ((hi - lo) >> 1);
+        const int axis = depth % 3;
+        bool go_far = false;
+        double diff;
+        if (arriving_down) {
+            double x, y, z;
+            int idx;
+            load_node(nodes, mid, x, y, z, idx);
+            // operand order root - target (utils/kdtree.c:16); squared, so the sign is immaterial
+            const double d = dsq3(dsub(x, qx), dsub(y, qy), dsub(z, qz));
+            if (d < best || (d == best && idx < bidx)) {
+                best = d;
+                bidx = idx;
+            }
+            diff = dsub(axis == 0 ? qx : (axis == 1 ? qy : qz), axis == 0 ? x : (axis == 1 ? y : z));
+            const bool near_right = !(diff < 0.0);  // target < node -> left, else right (kdtree.c:130-141)
+            par = (par & ~(1u << depth)) | ((unsigned)((hi - lo) & 1) << depth);
+            // near child
+            const int clo = near_right ? mid + 1 : lo, chi = near_right ? hi : mid;
+            if (clo < chi) {
+                path = (path & ~(1u << depth)) | ((unsigned)near_right << depth);
+                lo = clo;
+                hi = chi;
+                ++depth;
+                continue;
+            }
+            // empty near child: fall through as if we had just come back from it
+            go_far = true;
+            path = (path & ~(1u << depth)) | ((unsigned)near_right << depth);
+        } else {
+            const double key = node_axis(nodes, mid, axis);
+            diff = dsub(axis == 0 ? qx : (axis == 1 ? qy : qz), key);
+            const bool near_right = !(diff < 0.0);
+            const bool from_right = (path >> depth) & 1u;
+            go_far = from_right == near_right;  // came back from the near side
+        }
+        if (go_far) {
+            const bool near_right = (path >> depth) & 1u;
+            const int clo = near_right ? lo : mid + 1, chi = near_right ? mid : hi;
+            const double plane = dmul(diff, diff);
+            // the reference prunes with |delta| < best (kdtree.c:147); '<=' on squares also keeps
+            // exact ties reachable so the lowest index wins; NaN planes are never pruned
+            if (clo < chi && !(plane > best)) {
+                path ^= (1u << depth);
+                lo = clo;
+                hi = chi;
+                ++depth;
+                arriving_down = true;
+                continue;
+            }
+        }
+        // this node is finished: climb
+        if (depth == 0) break;
+        --depth;
+        const int cs = hi - lo;
+        const unsigned parity = (par >> depth) & 1u;
+        if ((path >> depth) & 1u) {  // we are the right child
+            const int s = 2 * cs + 1 + (parity ? 0 : 1);
+            lo = hi - s;
+        } else {
+            const int s = 2 * cs + (int)parity;
+            hi = lo + s;
+        }
+        arriving_down = false;
+    }
+    idx_out[qi] = bidx;
+    dist_out[qi] = bidx >= 0 ? __dsqrt_rn(best) : INFINITY;
+}
+
+cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_queries, size_t nq, int *d_idx,
+                  double *d_dist, cudaStream_t stream, uint64_t *launches) {
+    if (nq == 0) return cudaSuccess;
+    const int threads = 128;
+    const unsigned grid = (unsigned)((nq + threads - 1) / threads);
+    k_kd_nn<<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, d_idx, d_dist);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// --------------------------------------------------------------- exact fp64 brute force ------
+constexpr int kBfTile = 1024;
+__global__ void __launch_bounds__(256)
+k_bf_nn(const double *__restrict__ pts, long long n, const double *__restrict__ queries, long long nq,
+        int *__restrict__ idx_out, double *__restrict__ dist_out) {
+    __shared__ double s_p[kBfTile * 3];
+    const long long qi = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool live = qi < nq;
+    double qx = 0, qy = 0, qz = 0;
+    if (live) {
+        qx = queries[qi * 3];
+        qy = queries[qi * 3 + 1];
+        qz = queries[qi * 3 + 2];
+    }
+    double best = INFINITY;
+    int bidx = -1;
+    for (long long t0 = 0; t0 < n; t0 += kBfTile) {
+        const int cnt = (int)min((long long)kBfTile, n - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 3; i += blockDim.x) s_p[i] = pts[t0 * 3 + i];
+        __syncthreads();
+        if (live) {
+            for (int j = 0; j < cnt; ++j) {
+                const double d = dsq3(dsub(s_p[j * 3], qx), dsub(s_p[j * 3 + 1], qy), dsub(s_p[j * 3 + 2], qz));
+                if (d < best) {  // ascending index scan: strict '<' keeps the lowest index
+                    best = d;
+                    bidx = (int)(t0 + j);
+                }
+            }
+        }
+    }
+    if (live) {
+        idx_out[qi] = bidx;
+        dist_out[qi] = bidx >= 0 ? __dsqrt_rn(best) : INFINITY;
+    }
+}
+
+cudaError_t bf_nn(const double *d_pts, size_t n, const double *d_queries, size_t nq, int *d_idx, double *d_dist,
+                  cudaStream_t stream) {
+    if (nq == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((nq + 255) / 256);
+    k_bf_nn<<<grid, 256, 0, stream>>>(d_pts, (long long)n, d_queries, (long long)nq, d_idx, d_dist);
+    return cudaGetLastError();
+}
+
+}  // namespace nav

@@ -1,0 +1,21 @@
+// nav_kdtree.cuh -- flat kd-tree interfaces (kdtree.cu)
+#pragma once
+#include "nav_common.cuh"
+
+namespace nav {
+
+struct __align__(32) KdNode {
+    double x, y, z;
+    int idx;  // index of the point in the build input
+    int pad;
+};
+static_assert(sizeof(KdNode) == 32, "one DRAM sector per node");
+
+cudaError_t kd_build(const double *d_pts, size_t n, KdNode *d_nodes, int sm_count, cudaStream_t stream,
+                     uint64_t *launches);
+cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_queries, size_t nq, int *d_idx,
+                  double *d_dist, cudaStream_t stream, uint64_t *launches);
+cudaError_t bf_nn(const double *d_pts, size_t n, const double *d_queries, size_t nq, int *d_idx, double *d_dist,
+                  cudaStream_t stream);
+
+}  // namespace nav

@@ -1,0 +1,371 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/navslam_b200.h), against the
+CPU oracle on the same seeded inputs.  Integer / index outputs and all binary64 values are
+compared bit-for-bit (np.array_equal), which is tighter than north_star's 1e-5 tolerance for
+curvature and distances."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(8, 8), (5, 33), (16, 1800), (64, 2048)]
+
+
+def _cloud(synth, shape, frame=0, **kw):
+    r, c = shape
+    if shape == (16, 1800):
+        return synth.room_frame(r, c, frame, cfg=2, elev=(-15, 15), integer_mm=True, **kw)
+    return synth.room_frame(r, c, frame, **kw)
+
+
+@pytest.fixture(scope="module")
+def ctxs(pkg):
+    made = {}
+
+    def get(shape, n_seq=1):
+        key = (shape, n_seq)
+        if key not in made:
+            made[key] = pkg.Context(shape[0], shape[1], device=0, n_seq=n_seq)
+        return made[key]
+
+    yield get
+    for c in made.values():
+        c.close()
+
+
+# ------------------------------------------------------------------ a3 -----------------------
+@pytest.mark.parametrize("shape", SHAPES + [(3, 4), (2, 5), (7, 300)])
+def test_labels_and_curvature_bit_exact(ctxs, oracle, synth, shape):
+    ctx = ctxs(shape)
+    for frame, inv in ((0, 0.0), (5, 0.03)):
+        cloud = _cloud(synth, shape, frame, invalid_frac=inv)
+        assert np.array_equal(ctx.extract_feature(cloud), oracle.extract_feature(cloud))
+        assert np.array_equal(ctx.curvature(cloud), oracle.curvature(cloud))
+
+
+def test_labels_only_sets_ones(ctxs, oracle, synth):
+    shape = (5, 33)
+    cloud = _cloud(synth, shape, 2)
+    pre = np.full(shape, 7, dtype=np.int32)
+    got = ctxs(shape).extract_feature(cloud, pre.copy())
+    want = oracle.extract_feature(cloud, pre.copy())
+    assert np.array_equal(got, want) and set(np.unique(got)) <= {1, 7}
+
+
+def test_labels_special_values(ctxs, oracle):
+    rng = np.random.default_rng(7)
+    cloud = rng.normal(0, 1000, size=(5, 33, 3))
+    cloud[0, 5] = np.nan
+    cloud[1, 7] = np.inf
+    cloud[2, 10:20] = 0.0
+    cloud[3, :] = cloud[3, 0]
+    cloud[4, 10:14] = 1e-200
+    cloud[4, 20:24] = 1e200
+    ctx = ctxs((5, 33))
+    assert np.array_equal(ctx.extract_feature(cloud), oracle.extract_feature(cloud))
+    assert np.array_equal(ctx.curvature(cloud), oracle.curvature(cloud), equal_nan=True)
+
+
+def test_labels_near_threshold(ctxs, oracle):
+    """Points engineered to sit within ~1e-12 of the 0.1 threshold on both sides."""
+    rng = np.random.default_rng(3)
+    rows, cols = 5, 33
+    cloud = np.zeros((rows, cols, 3))
+    # collinear with spacing pattern s, s, t, t around each point: tune t so curvature ~ 0.1
+    for r in range(rows):
+        x = np.cumsum(rng.uniform(90, 110, size=cols))
+        cloud[r, :, 0] = x
+        cloud[r, :, 1] = rng.normal(0, 2.0, size=cols)
+    ctx = ctxs((rows, cols))
+    base = oracle.curvature(cloud)
+    # bisect one coordinate of the centre point so its curvature straddles 0.1
+    r, c = 2, 16
+    lo, hi = -200.0, 200.0
+    for _ in range(200):
+        mid = 0.5 * (lo + hi)
+        cloud[r, c, 1] = mid
+        v = oracle.curvature(cloud)[r, c]
+        if v > 0.1:
+            hi = mid
+        else:
+            lo = mid
+    for y in (lo, hi, np.nextafter(lo, -np.inf), np.nextafter(hi, np.inf)):
+        cloud[r, c, 1] = y
+        assert np.array_equal(ctx.extract_feature(cloud), oracle.extract_feature(cloud))
+        assert np.array_equal(ctx.curvature(cloud), oracle.curvature(cloud))
+    del base
+
+
+def test_labels_batch_dev(pkg, ctxs, oracle, synth):
+    torch = pytest.importorskip("torch")
+    shape = (16, 1800)
+    ctx = ctxs(shape)
+    frames = np.stack([_cloud(synth, shape, f) for f in range(5)])
+    d_clouds = torch.from_numpy(frames).cuda()
+    d_labels = torch.empty(frames.shape[:-1], dtype=torch.int32, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.extract_feature_batch_dev(d_clouds.data_ptr(), frames.shape[0], d_labels.data_ptr())
+    torch.cuda.synchronize()
+    ctx.set_stream(None)
+    got = d_labels.cpu().numpy()
+    for f in range(frames.shape[0]):
+        assert np.array_equal(got[f], oracle.extract_feature(frames[f]))
+
+
+# ------------------------------------------------------------------ a2 / a4 / a7 -------------
+@pytest.mark.parametrize("shape", [(8, 8), (5, 33), (16, 1800)])
+def test_convert_bit_exact(ctxs, oracle, shape):
+    rng = np.random.default_rng(11)
+    d = rng.integers(-5, 4000, size=shape).astype(np.int32)
+    d[0, 0] = 0
+    assert np.array_equal(ctxs(shape).convert_to_pointcloud(d), oracle.convert(d))
+
+
+@pytest.mark.parametrize("shape", [(5, 33), (64, 2048)])
+def test_transform_bit_exact(ctxs, oracle, synth, shape):
+    rng = np.random.default_rng(5)
+    cloud = _cloud(synth, shape, 1)
+    for _ in range(3):
+        pos = np.concatenate([rng.normal(0, 5000, 3), rng.uniform(-180, 180, 3)])
+        assert np.array_equal(ctxs(shape).transform_cloud(cloud, pos), oracle.transform(cloud, pos))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_flatten_bit_exact(ctxs, oracle, synth, shape):
+    cloud = _cloud(synth, shape, 1)
+    feat = oracle.extract_feature(cloud)
+    feat[0, 0] = 1
+    feat[0, 1] = 2
+    feat[-1, -1] = 1
+    ctx = ctxs(shape)
+    for r in (0, shape[0] - 1):
+        assert np.array_equal(ctx.flatten_points(cloud[r], feat[r]), oracle.flatten(cloud[r], feat[r]))
+    none = np.zeros(shape[1], dtype=np.int32)
+    assert ctx.flatten_points(cloud[0], none).shape == (0, 3)
+    assert np.array_equal(ctx.flatten_points(cloud[0], none + 1), cloud[0])
+
+
+# ------------------------------------------------------------------ frame path (a3+a7+a4+a5+a6)
+@pytest.mark.parametrize("shape,frames", [((8, 8), 6), ((5, 33), 6), ((16, 1800), 4), ((64, 2048), 3)])
+def test_frontend_frames_bit_exact(ctxs, oracle, synth, shape, frames):
+    r, c = shape
+    ctx = ctxs(shape)
+    slam = oracle.slam(r, c, 1)
+    rng = np.random.default_rng(17)
+    if shape == (8, 8):
+        clouds = [oracle.convert(synth.l5_depth_frame(f)) for f in range(frames)]
+    else:
+        clouds = [_cloud(synth, shape, f, invalid_frac=0.01 if f == 2 else 0.0) for f in range(frames)]
+    pos = np.array([10.0, -20.0, 5.0, 1.0, -2.0, 30.0])
+    assert np.array_equal(ctx.slam_init(pos, clouds[0]), slam.init(pos, clouds[0]))
+    for row in (0, r - 1):
+        pts, col = ctx.row_map_export(row)
+        feat0 = oracle.extract_feature(clouds[0])
+        assert np.array_equal(col, np.nonzero(feat0[row] == 1)[0])
+    last = pos
+    for f in range(1, frames):
+        pred = last + np.concatenate([rng.normal(45, 5, 1), rng.normal(0, 3, 2), rng.normal(0, 0.3, 3)])
+        final = pred + np.concatenate([rng.normal(0, 2, 3), rng.normal(0, 0.05, 3)])
+        feat, idx, dist, g = ctx.frontend_frame(clouds[f], pred, last, final)
+        ofeat, oidx, odist, og = slam.frontend_frame(clouds[f], pred, last, final)
+        assert np.array_equal(feat, ofeat)
+        assert np.array_equal(idx, oidx), (f, np.nonzero(idx != oidx))
+        assert np.array_equal(dist, odist)
+        assert np.array_equal(g, og)
+        last = final
+    slam.close()
+
+
+def test_frontend_empty_rows_and_no_features(ctxs, oracle):
+    """Rows whose previous frame had no edge points (NULL tree in the reference) and frames with
+    no labelled points at all."""
+    shape = (5, 33)
+    ctx = ctxs(shape)
+    slam = oracle.slam(*shape, 1)
+    rng = np.random.default_rng(1)
+    flat = np.zeros((5, 33, 3))
+    flat[..., 0] = 1000.0  # all points identical -> avg 0 -> no labels anywhere
+    noisy = rng.normal(0, 1000, size=(5, 33, 3))
+    z = np.zeros(6)
+    assert np.array_equal(ctx.slam_init(z, flat), slam.init(z, flat))
+    a = ctx.frontend_frame(noisy, z, z, z)
+    b = slam.frontend_frame(noisy, z, z, z)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert (a[1] == -1).all() and np.isinf(a[2][a[0] == 1]).all()
+    a = ctx.frontend_frame(flat, z, z, z)
+    b = slam.frontend_frame(flat, z, z, z)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert a[0].sum() == 0
+    slam.close()
+
+
+def test_frontend_multi_sequence(pkg, oracle, synth):
+    """n_seq sequences side by side give exactly what n_seq separate contexts give."""
+    shape, n_seq = (16, 1800), 3
+    ctx = pkg.Context(*shape, device=0, n_seq=n_seq)
+    slams = [oracle.slam(*shape, 1) for _ in range(n_seq)]
+    clouds = [np.stack([synth.room_frame(*shape, f, seq=s) for s in range(n_seq)]) for f in range(3)]
+    pos0 = np.stack([np.array([100.0 * s, 0, 0, 0, 0, 1.0 * s]) for s in range(n_seq)])
+    g = ctx.slam_init(pos0, clouds[0])
+    for s in range(n_seq):
+        assert np.array_equal(g[s], slams[s].init(pos0[s], clouds[0][s]))
+    last = pos0
+    for f in (1, 2):
+        pred = last + np.array([50.0, 1.0, 0.0, 0.0, 0.0, 0.1])
+        final = pred + np.array([0.5, -0.5, 0.1, 0.0, 0.0, 0.0])
+        feat, idx, dist, g = ctx.frontend_frame(clouds[f], pred, last, final)
+        for s in range(n_seq):
+            ofeat, oidx, odist, og = slams[s].frontend_frame(clouds[f][s], pred[s], last[s], final[s])
+            assert np.array_equal(feat[s], ofeat) and np.array_equal(idx[s], oidx)
+            assert np.array_equal(dist[s], odist) and np.array_equal(g[s], og)
+        last = final
+    ctx.close()
+    for s in slams:
+        s.close()
+
+
+# ------------------------------------------------------------------ whole step (a8 + Adam) ---
+@pytest.mark.parametrize("shape,frames", [((8, 8), 8), ((5, 33), 6), ((16, 1800), 3), ((64, 2048), 2)])
+def test_slam_step_bit_exact(ctxs, oracle, synth, shape, frames):
+    r, c = shape
+    ctx = ctxs(shape)
+    slam = oracle.slam(r, c, 1)
+    if shape == (8, 8):
+        clouds = [oracle.convert(synth.l5_depth_frame(f)) for f in range(frames)]
+    else:
+        clouds = [_cloud(synth, shape, f) for f in range(frames)]
+    pos = np.array([10.0, -20.0, 5.0, 1.0, -2.0, 30.0])
+    assert np.array_equal(ctx.slam_init(pos, clouds[0]), slam.init(pos, clouds[0]))
+    last = pos
+    for f in range(1, frames):
+        pred = last + np.array([45.0, 3.0, -1.0, 0.0, 0.0, 0.0])
+        corr = ctx.slam_match(clouds[f], pred, last)
+        p_gpu, err_gpu = ctx.slam_localization(clouds[f], pred, last)
+        p_or, corr_or, err_or, _ = slam.localize(clouds[f], pred, last)
+        assert corr.shape == corr_or.shape
+        assert np.array_equal(corr, corr_or)
+        assert np.array_equal(p_gpu, p_or) and err_gpu == err_or
+        g = ctx.slam_mapping(p_gpu, None)           # reuse the resident frame
+        g2 = ctx.slam_mapping(p_gpu, clouds[f])     # strict re-upload, same answer
+        og = slam.map(p_or, clouds[f])
+        assert np.array_equal(g, og) and np.array_equal(g2, og)
+        last = p_gpu
+    slam.close()
+
+
+# ------------------------------------------------------------------ kd-tree (a5 / a6) --------
+def _check_inorder(nodes, lo, hi, depth, bounds):
+    """Recursive invariant check of the in-order layout: left keys <= node key <= right keys."""
+    stack = [(lo, hi, depth)]
+    while stack:
+        lo, hi, d = stack.pop()
+        if hi - lo <= 1:
+            continue
+        mid = lo + (hi - lo) // 2
+        a = d % 3
+        k = nodes[mid, a]
+        assert (nodes[lo:mid, a] <= k).all() and (nodes[mid + 1:hi, a] >= k).all()
+        stack.append((lo, mid, d + 1))
+        stack.append((mid + 1, hi, d + 1))
+
+
+@pytest.mark.parametrize("kind", ["uniform", "clustered", "integer", "duplicates", "sorted", "all_equal"])
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 1000, 30000])
+def test_kdtree_exact_lowest_index(pkg, oracle, synth, kind, n):
+    rng = np.random.default_rng(n + 13)
+    if kind == "uniform":
+        pts = synth.map_points(n, seed=n)
+    elif kind == "clustered":
+        pts = synth.map_points(n, variant="clustered", seed=n)
+    elif kind == "integer":
+        pts = rng.integers(0, 40, size=(n, 3)).astype(np.float64)
+    elif kind == "duplicates":
+        pts = np.repeat(rng.normal(0, 100, size=((n + 3) // 4, 3)), 4, axis=0)[:n]
+    elif kind == "sorted":
+        pts = np.stack([np.arange(n, dtype=np.float64)] * 3, axis=1)
+    else:
+        pts = np.full((n, 3), 3.25)
+    tree = pkg.KdTree(pts, device=0)
+    assert len(tree) == n
+    nodes, oidx = tree.export()
+    if n:
+        assert np.array_equal(np.sort(oidx), np.arange(n))
+        assert np.array_equal(nodes, pts[oidx])
+        _check_inorder(nodes, 0, n, 0, None)
+    nq = 500
+    q = (pts[rng.integers(0, n, size=nq)] + rng.normal(0, 3, size=(nq, 3))) if n else rng.normal(size=(nq, 3))
+    if kind in ("integer", "all_equal"):
+        q = np.rint(q)
+    idx, dist, near = tree.nn_batch(q)
+    oi, od = oracle.nn_brute(pts, q)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist, od)
+    if n:
+        assert np.array_equal(near, pts[oi])
+    tree.close()
+
+
+def test_kdtree_same_tree_as_reference_when_keys_distinct(pkg, oracle, synth):
+    """With distinct keys the median-split tree is unique, so our flat in-order array must be the
+    array the reference's in-place recursion leaves behind (utils/kdtree.c:65-82)."""
+    pts = synth.map_points(5000, seed=77)
+    h, perm = oracle.tree_build(pts)
+    oracle.tree_free(h)
+    tree = pkg.KdTree(pts, device=0)
+    nodes, _ = tree.export()
+    assert np.array_equal(nodes, perm)
+    tree.close()
+
+
+def test_kdtree_special_values(pkg, oracle):
+    rng = np.random.default_rng(2)
+    pts = rng.normal(0, 100, size=(2000, 3))
+    pts[5] = np.nan
+    pts[6, 1] = np.nan
+    pts[7] = np.inf
+    pts[8] = -np.inf
+    pts[9] = 0.0
+    pts[10] = -0.0
+    q = rng.normal(0, 100, size=(300, 3))
+    q[0] = 0.0
+    tree = pkg.KdTree(pts, device=0)
+    idx, dist, _ = tree.nn_batch(q)
+    oi, od = oracle.nn_brute(pts, q)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    tree.close()
+
+
+def test_kdtree_1m_vs_bruteforce(pkg, oracle, synth):
+    """Config 4 size: 1 M-point map, 131 072 queries.  Checked against the exact fp64 brute-force
+    kernel on a 4096-query subset and against the CPU oracle on 64 queries; all queries must
+    return a point at the reported distance."""
+    torch = pytest.importorskip("torch")
+    for variant, qvar in (("uniform", "jitter"), ("clustered", "uniform")):
+        pts = synth.map_points(1_000_000, variant=variant)
+        q = synth.map_queries(pts, 131072, variant=qvar)
+        tree = pkg.KdTree(pts, device=0)
+        idx, dist, near = tree.nn_batch(q)
+        d_back = np.sqrt(((near - q) ** 2)[:, 0] + ((near - q) ** 2)[:, 1] + ((near - q) ** 2)[:, 2])
+        assert np.array_equal(near, pts[idx])
+        assert np.array_equal(d_back, dist)
+        sub = slice(0, 4096)
+        d_pts = torch.from_numpy(pts).cuda()
+        d_q = torch.from_numpy(q[sub]).cuda()
+        d_idx = torch.empty(4096, dtype=torch.int32, device="cuda")
+        d_dist = torch.empty(4096, dtype=torch.float64, device="cuda")
+        pkg.bruteforce_nn_dev(0, d_pts.data_ptr(), pts.shape[0], d_q.data_ptr(), 4096, d_idx.data_ptr(),
+                              d_dist.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_idx.cpu().numpy(), idx[sub])
+        assert np.array_equal(d_dist.cpu().numpy(), dist[sub])
+        oi, od = oracle.nn_brute(pts, q[:64])
+        assert np.array_equal(oi, idx[:64]) and np.array_equal(od, dist[:64])
+        tree.close()
+
+
+def test_no_device_errors_are_loud(pkg):
+    with pytest.raises(pkg.NavError):
+        pkg.Context(8, 8, device=99)
+    with pytest.raises(pkg.NavError):
+        pkg.Context(8, 8, device=0, n_seq=1000)
