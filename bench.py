@@ -244,7 +244,8 @@ def run_gpu_arm(args):
     frames = make_frames(pkg, n_frames, seq=rank)  # [F,64,2048,3] fp64, 3.1 MB each
     L = pkg.load_library()
     ctx = pkg.Context(ROWS, COLS, device=local, n_seq=1)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()           # a real (non-default) stream: events and kernels share it
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     d_frames = torch.from_numpy(frames).cuda()

@@ -60,7 +60,9 @@ nav_ctx *nav_create(int rows, int cols, int device, int n_seq);
 void nav_destroy(nav_ctx *ctx);
 int nav_rows(const nav_ctx *ctx);
 int nav_cols(const nav_ctx *ctx);
-int nav_set_stream(nav_ctx *ctx, void *cuda_stream); /* run on the caller's cudaStream_t (NULL = own stream) */
+/* use_own != 0: back to the context's own non-blocking stream; otherwise run on the caller's
+ * cudaStream_t (0 = the legacy default stream) */
+int nav_set_stream(nav_ctx *ctx, void *cuda_stream, int use_own);
 int nav_synchronize(nav_ctx *ctx);
 /* number of kernels this library has launched on behalf of ctx since creation */
 uint64_t nav_launch_count(const nav_ctx *ctx);
@@ -82,6 +84,7 @@ int nav_transform_cloud(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos
 /* ---- kd-tree, replaces utils/kdtree.h:21-27 ---------------------------------------- */
 /* Build from n host points (the caller's array is NOT permuted; idx refers to it). */
 nav_kdtree *nav_kdtree_build(int device, const nav_point *points, size_t n);
+/* the *_dev entry points run on the given cudaStream_t (0 = legacy default stream) and do not synchronise */
 nav_kdtree *nav_kdtree_build_dev(int device, const void *dev_points, size_t n, void *cuda_stream);
 void nav_kdtree_free(nav_kdtree *tree);
 size_t nav_kdtree_size(const nav_kdtree *tree);

@@ -71,7 +71,7 @@ def load_library(build_if_missing: bool = True):
     L.nav_destroy.argtypes = [C.c_void_p]
     L.nav_rows.argtypes = [C.c_void_p]
     L.nav_cols.argtypes = [C.c_void_p]
-    L.nav_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.nav_set_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.nav_synchronize.argtypes = [C.c_void_p]
     L.nav_launch_count.restype = C.c_uint64
     L.nav_launch_count.argtypes = [C.c_void_p]
@@ -243,7 +243,11 @@ class Context:
 
     # ---- device resident (raw device pointers, e.g. torch tensor .data_ptr())
     def set_stream(self, cuda_stream_handle):
-        _check(self.L.nav_set_stream(self.h, cuda_stream_handle), self.L)
+        """Run on the caller's cudaStream_t (0 = legacy default stream); None = the context's own stream."""
+        if cuda_stream_handle is None:
+            _check(self.L.nav_set_stream(self.h, None, 1), self.L)
+        else:
+            _check(self.L.nav_set_stream(self.h, cuda_stream_handle, 0), self.L)
 
     def synchronize(self):
         _check(self.L.nav_synchronize(self.h), self.L)

@@ -368,10 +368,11 @@ extern "C" int nav_rows(const nav_ctx *c) { return c ? c->rows : 0; }
 extern "C" int nav_cols(const nav_ctx *c) { return c ? c->cols : 0; }
 extern "C" uint64_t nav_launch_count(const nav_ctx *c) { return c ? c->launches : 0; }
 
-extern "C" int nav_set_stream(nav_ctx *c, void *s) {
+extern "C" int nav_set_stream(nav_ctx *c, void *s, int use_own) {
     if (!c) return fail("nav_set_stream: null context");
+    CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    c->stream = use_own ? c->own_stream : (cudaStream_t)s;  // s == 0 is the legacy default stream
     return 0;
 }
 
@@ -796,7 +797,7 @@ extern "C" nav_kdtree *nav_kdtree_build_dev(int device, const void *dev_points, 
     }
     nav_kdtree *t = kd_new(device, n);
     if (!t) return nullptr;
-    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : t->stream;
+    cudaStream_t s = (cudaStream_t)cuda_stream;  // 0 = legacy default stream
     cudaError_t e = cudaSuccess;
     if (n) {
         e = cudaMemcpyAsync(t->d_pts, dev_points, n * 24, cudaMemcpyDeviceToDevice, s);
@@ -852,7 +853,7 @@ extern "C" int nav_kdtree_nn_batch_dev(nav_kdtree *t, const void *dev_queries, s
     if (!t) return fail("nav_kdtree_nn_batch_dev: null tree");
     if (nq && (!dev_queries || !dev_idx || !dev_dist)) return fail("nav_kdtree_nn_batch_dev: null argument");
     CU(cudaSetDevice(t->device));
-    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : t->stream;
+    cudaStream_t s = (cudaStream_t)cuda_stream;  // 0 = legacy default stream
     CU(kd_nn(t->d_nodes, t->n, (const double *)dev_queries, nq, (int *)dev_idx, (double *)dev_dist, s, &t->launches));
     return 0;
 }

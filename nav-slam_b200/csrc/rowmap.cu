@@ -334,13 +334,18 @@ k_match(const double *__restrict__ cloud, const int *__restrict__ labels, RowMap
     if (threadIdx.x == 0) out.corr_row_count[rid] = n_out;
 }
 
+// The attribute is per function and per device, not per context: only ever raise it.
 int configure_row_kernels(int cols) {
+    static int configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int need = (int)match_smem_bytes(cols, true);
+    if (dev >= 0 && dev < 64 && configured[dev] >= need) return 0;
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)match_smem_bytes(cols, true));
+    e = cudaFuncSetAttribute(k_match<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)match_smem_bytes(cols, false));
+    e = cudaFuncSetAttribute(k_match<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) configured[dev] = need;
     return (int)e;
 }
 
