@@ -321,10 +321,14 @@ def run_gpu_arm(args):
     h_feat_np = h_feat.numpy()
     nq = int((h_feat_np == 1).sum())
     n_map = nq  # consecutive frames label ~the same number of points
+    n_leaf, n_sup = COLS // 16, COLS // 256
+    side = ROWS * (n_leaf * 52 + n_sup * 48)                   # label masks + leaf boxes + super boxes
     alg_bytes = {
         "labels": NPX * 28,                                   # 24 B point read + 4 B label write
-        "match": NPX * 4 + nq * 24 + NPX * 12 + n_map * 24,   # labels + query points + (idx,dist) + row maps
-        "map": NPX * (24 + 4 + 24) + n_map * (24 + 4) + NPX * 4,  # cloud+labels in, global out, map+col+rank out
+        # fused labels+match: cloud in, labels out, (idx,dist) out, map points + masks/boxes in
+        "match": NPX * (24 + 4 + 12) + n_map * 24 + side,
+        # transform + map build: cloud + labels in, global cloud out, masks/boxes out
+        "map": NPX * (24 + 4 + 24) + side,
     }
     peak, peak_src = measured_peaks()
     kernels = {}

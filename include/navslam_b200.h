@@ -140,7 +140,7 @@ typedef struct {
     void *nn_idx;   /* int32  [n_seq][rows][cols] */
     void *nn_dist;  /* double [n_seq][rows][cols] */
     void *global;   /* point  [n_seq][rows][cols] */
-    void *map_count;/* int32  [n_seq][rows]  labelled points per row of the frame just mapped */
+    void *map_mask; /* uint32 [n_seq][rows][ceil(cols/16)] edge-point bit masks of the frame just mapped */
 } nav_frame_results;
 int nav_frame_results_dev(nav_ctx *ctx, nav_frame_results *out);
 
@@ -148,6 +148,10 @@ int nav_frame_results_dev(nav_ctx *ctx, nav_frame_results *out);
  * frame mapped last, compacted in column order (= the flattenedPoints array of src/slam.c:170-171),
  * and the column each came from.  pts_out needs room for cols points; col_out may be NULL. */
 int nav_row_map_export(nav_ctx *ctx, int seq, int row, nav_point *pts_out, int32_t *col_out, size_t *n_out);
+
+/* how many labels the fp32 filter of the curvature stencil could not decide and re-evaluated with
+ * the reference's exact binary64 arithmetic since the context was created (statistics only) */
+uint64_t nav_exact_fallback_count(nav_ctx *ctx);
 
 /* per-kernel device time accumulated with CUDA events on the context's stream (enable first) */
 int nav_profile_enable(nav_ctx *ctx, int on);

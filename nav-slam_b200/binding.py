@@ -23,7 +23,7 @@ class NavPos(C.Structure):
 
 
 class NavFrameResults(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("labels", "nn_idx", "nn_dist", "global_", "map_count")]
+    _fields_ = [(n, C.c_void_p) for n in ("labels", "nn_idx", "nn_dist", "global_", "map_mask")]
 
 
 class NavError(RuntimeError):
@@ -43,6 +43,7 @@ EXPORTS = [
     "nav_slam_match", "nav_slam_localization", "nav_slam_mapping", "nav_frontend_frame",
     "nav_extract_feature_batch_dev", "nav_frontend_frame_dev", "nav_slam_init_dev",
     "nav_frame_results_dev", "nav_profile_enable", "nav_profile_read", "nav_row_map_export",
+    "nav_exact_fallback_count",
 ]
 
 
@@ -107,6 +108,8 @@ def load_library(build_if_missing: bool = True):
     L.nav_frontend_frame_dev.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos)]
     L.nav_frame_results_dev.argtypes = [vp, C.POINTER(NavFrameResults)]
     L.nav_row_map_export.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_size_t)]
+    L.nav_exact_fallback_count.restype = C.c_uint64
+    L.nav_exact_fallback_count.argtypes = [vp]
     L.nav_profile_enable.argtypes = [vp, C.c_int]
     L.nav_profile_read.argtypes = [vp, C.c_char_p, c_double_p, C.POINTER(C.c_uint64), C.c_int]
     _LIB = L
@@ -274,6 +277,9 @@ class Context:
         n = C.c_size_t(0)
         _check(self.L.nav_row_map_export(self.h, seq, row, pts.ctypes.data, col.ctypes.data, C.byref(n)), self.L)
         return pts[:n.value].copy(), col[:n.value].copy()
+
+    def exact_fallback_count(self) -> int:
+        return int(self.L.nav_exact_fallback_count(self.h))
 
     def launch_count(self) -> int:
         return int(self.L.nav_launch_count(self.h))

@@ -161,6 +161,7 @@ struct nav_ctx {
     size_t npx = 0, ntot = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     double *d_cloud = nullptr, *d_global = nullptr, *d_curv = nullptr, *d_nn_dist = nullptr;
+    unsigned *d_n_exact = nullptr;  // labels the fp32 filter could not decide (exact re-evaluations)
     int *d_labels = nullptr, *d_nn_idx = nullptr;
     RowMap map = {};
     nav_corr *d_corr_rows = nullptr, *d_corr = nullptr;
@@ -244,7 +245,7 @@ extern "C" void nav_destroy(nav_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->d_cloud, c->d_global, c->d_curv, c->d_nn_dist, c->d_labels, c->d_nn_idx, c->map.pts,
-                    c->map.col, c->map.rank, c->map.count, c->map.box, c->map.sbox, c->d_corr_rows, c->d_corr,
+                    c->map.mask, c->d_n_exact, c->map.box, c->map.sbox, c->d_corr_rows, c->d_corr,
                     c->d_corr_row_count, c->d_corr_total, c->d_dist, c->d_tan_col, c->d_tan_row, c->d_flat,
                     c->d_flat_count};
     for (void *p : ptrs)
@@ -285,9 +286,9 @@ extern "C" nav_ctx *nav_create(int rows, int cols, int device, int n_seq) {
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    if (match_smem_bytes(cols, true) > (size_t)max_smem) {
+    if (dedupe_smem_bytes(cols) > (size_t)max_smem) {
         fail("nav_create: %d columns need %zu B of shared memory per row CTA, device allows %d", cols,
-             match_smem_bytes(cols, true), max_smem);
+             dedupe_smem_bytes(cols), max_smem);
         delete c;
         return nullptr;
     }
@@ -307,14 +308,12 @@ extern "C" nav_ctx *nav_create(int rows, int cols, int device, int n_seq) {
     c->map.n_chunks = div_up(cols, kChunk);
     c->map.n_super = div_up(c->map.n_chunks, kChunksPerSuper);
     ALLOC(c->d_cloud, nt * 24);
-    ALLOC(c->d_global, nt * 24);
     ALLOC(c->d_labels, nt * 4);
     ALLOC(c->d_nn_idx, nt * 4);
     ALLOC(c->d_nn_dist, nt * 8);
     ALLOC(c->map.pts, nt * 24);
-    ALLOC(c->map.col, nt * 4);
-    ALLOC(c->map.rank, nt * 4);
-    ALLOC(c->map.count, nr * 4);
+    ALLOC(c->map.mask, nr * c->map.n_chunks * 4);
+    ALLOC(c->d_n_exact, 4);
     ALLOC(c->map.box, nr * c->map.n_chunks * 48);
     ALLOC(c->map.sbox, nr * c->map.n_super * 48);
     ALLOC(c->d_corr_rows, nt * sizeof(nav_corr));
@@ -324,10 +323,11 @@ extern "C" nav_ctx *nav_create(int rows, int cols, int device, int n_seq) {
     ALLOC(c->d_dist, c->npx * 4);
     ALLOC(c->d_tan_col, (size_t)cols * 8);
     ALLOC(c->d_tan_row, (size_t)rows * 8);
-    ALLOC(c->d_flat, (size_t)cols * 24 * 2 + (size_t)cols * 4);
+    ALLOC(c->d_flat, (size_t)cols * 24 * 2 + (size_t)cols * 8);
     ALLOC(c->d_flat_count, 4);
 #undef ALLOC
-    cudaMemsetAsync(c->map.count, 0, nr * 4, c->stream);
+    cudaMemsetAsync(c->map.mask, 0, nr * c->map.n_chunks * 4, c->stream);
+    cudaMemsetAsync(c->d_n_exact, 0, 4, c->stream);
     if (cudaHostAlloc((void **)&c->h_small, 4096, cudaHostAllocDefault) != cudaSuccess) {
         fail("nav_create: pinned scratch allocation failed");
         nav_destroy(c);
@@ -352,7 +352,7 @@ extern "C" nav_ctx *nav_create(int rows, int cols, int device, int n_seq) {
         cudaMemcpy(c->d_tan_row, tr.data(), (size_t)rows * 8, cudaMemcpyHostToDevice);
     }
     if (configure_row_kernels(cols) != 0) {
-        fail("nav_create: cannot opt in to %zu B dynamic shared memory", match_smem_bytes(cols, true));
+        fail("nav_create: cannot opt in to %zu B dynamic shared memory", dedupe_smem_bytes(cols));
         nav_destroy(c);
         return nullptr;
     }
@@ -423,29 +423,33 @@ static int finish_call(nav_ctx *c, const char *name) {
 // device-side building blocks (no sync) -------------------------------------------------------
 static void run_labels(nav_ctx *c, const double *d_cloud, int *d_labels, double *d_curv, size_t n_images) {
     ProfScope ps(c, &c->prof_labels);
-    launch_labels(d_cloud, d_labels, d_curv, (long long)n_images * c->rows, c->cols, c->sm_count, c->stream);
+    launch_labels(d_cloud, d_labels, d_curv, (long long)n_images * c->rows, c->cols, c->sm_count, c->d_n_exact,
+                  c->stream);
     c->launches++;
 }
 
-static void run_map(nav_ctx *c, const double *d_cloud, const PoseBatch &poses, bool write_global) {
+// transform + label masks + boxes of the frame whose labels are in d_labels (a7 + a4/a5)
+static void run_map(nav_ctx *c, const double *d_cloud, const PoseBatch &poses) {
     ProfScope ps(c, &c->prof_map);
-    launch_map_build(d_cloud, c->d_labels, write_global ? c->d_global : nullptr, c->map, poses, c->n_seq,
-                     c->rows, c->cols, c->stream);
+    launch_frame_map(d_cloud, c->d_labels, c->map, poses, c->n_seq, c->rows, c->cols, c->stream);
     c->launches++;
     c->have_map = true;
 }
 
+// labels (a3, fused into the match kernel) + queries (a7) + exact per-row NN (a6) [+ dedupe (a8)]
 static void run_match(nav_ctx *c, const double *d_cloud, const PoseBatch &poses, bool dedupe) {
     MatchOut out = {c->d_nn_idx, c->d_nn_dist, c->d_corr_rows, c->d_corr_row_count};
     {
         ProfScope ps(c, &c->prof_match);
-        launch_match(d_cloud, c->d_labels, c->map, out, poses, c->n_seq, c->rows, c->cols, dedupe, c->stream);
+        launch_frame_match(d_cloud, c->d_labels, true, c->map, out, poses, c->n_seq, c->rows, c->cols,
+                           c->d_n_exact, c->stream);
         c->launches++;
     }
     if (dedupe) {
+        launch_dedupe(d_cloud, c->d_labels, c->map, out, poses, c->n_seq, c->rows, c->cols, c->stream);
         launch_gather_corr(c->d_corr_rows, c->d_corr_row_count, c->d_corr, c->d_corr_total, c->n_seq, c->rows,
                            c->cols, c->stream);
-        c->launches++;
+        c->launches += 2;
     }
 }
 
@@ -505,11 +509,11 @@ extern "C" int nav_flatten_points(nav_ctx *c, const nav_point *row_points, const
         return fail("nav_flatten_points: null argument");
     const size_t cols = c->cols;
     double *d_in = c->d_flat, *d_out = c->d_flat + cols * 3;
-    int *d_feat = (int *)(c->d_flat + cols * 6);
+    int *d_feat = (int *)(c->d_flat + cols * 6);  // followed by cols ints of column scratch
     if (c->stage.reserve(cols * 56 + 1024, c->stream)) return fail("nav_flatten_points: staging");
     if (c->stage.h2d(d_in, row_points, cols * 24, c->stream)) return fail("nav_flatten_points: H2D");
     if (c->stage.h2d(d_feat, row_feature, cols * 4, c->stream)) return fail("nav_flatten_points: H2D");
-    launch_flatten_row(d_in, d_feat, d_out, c->d_flat_count, c->cols, c->stream);
+    launch_flatten_row(d_in, d_feat, nullptr, d_out, nullptr, c->d_flat_count, c->cols, c->stream);
     c->launches++;
     CU(cudaMemcpyAsync(c->h_small, c->d_flat_count, 4, cudaMemcpyDeviceToHost, c->stream));
     unsigned char *tmp = c->stage.take(cols * 24, c->stream);
@@ -525,6 +529,7 @@ extern "C" int nav_flatten_points(nav_ctx *c, const nav_point *row_points, const
 extern "C" int nav_transform_cloud(nav_ctx *c, const nav_point *cloud, const nav_pos *pos, nav_point *global_out) {
     CTX_ENTER(c, "nav_transform_cloud");
     if (!cloud || !pos || !global_out) return fail("nav_transform_cloud: null argument");
+    if (!c->d_global) CU(cudaMalloc((void **)&c->d_global, c->npx * 24));
     if (c->stage.reserve(c->npx * 48 + 512, c->stream)) return fail("nav_transform_cloud: staging");
     if (c->stage.h2d(c->d_cloud, cloud, c->npx * 24, c->stream)) return fail("nav_transform_cloud: H2D");
     c->cloud_resident = false;
@@ -546,9 +551,9 @@ extern "C" int nav_slam_init(nav_ctx *c, const nav_pos *pos, const nav_point *cl
     if (c->stage.reserve(c->ntot * 48 + 1024, c->stream)) return fail("nav_slam_init: staging");
     if (upload_cloud(c, cloud, "nav_slam_init")) return 1;
     run_labels(c, c->d_cloud, c->d_labels, nullptr, c->n_seq);
-    run_map(c, c->d_cloud, pose_batch(c, pos, nullptr), true);
+    run_map(c, c->d_cloud, pose_batch(c, pos, nullptr));
     c->cloud_resident = true;
-    if (global_out && c->stage.d2h(global_out, c->d_global, c->ntot * 24, c->stream))
+    if (global_out && c->stage.d2h(global_out, c->map.pts, c->ntot * 24, c->stream))
         return fail("nav_slam_init: D2H");
     return finish_call(c, "nav_slam_init");
 }
@@ -557,7 +562,7 @@ extern "C" int nav_slam_init_dev(nav_ctx *c, const void *dev_cloud, const nav_po
     CTX_ENTER(c, "nav_slam_init_dev");
     if (!pos || !dev_cloud) return fail("nav_slam_init_dev: null argument");
     run_labels(c, (const double *)dev_cloud, c->d_labels, nullptr, c->n_seq);
-    run_map(c, (const double *)dev_cloud, pose_batch(c, pos, nullptr), true);
+    run_map(c, (const double *)dev_cloud, pose_batch(c, pos, nullptr));
     c->cloud_resident = false;
     CU(cudaGetLastError());
     return 0;
@@ -572,7 +577,6 @@ extern "C" int nav_slam_match(nav_ctx *c, const nav_point *cloud, const nav_pos 
     if (c->stage.reserve(c->ntot * 24 + c->ntot * sizeof(nav_corr) + 1024, c->stream))
         return fail("nav_slam_match: staging");
     if (upload_cloud(c, cloud, "nav_slam_match")) return 1;
-    run_labels(c, c->d_cloud, c->d_labels, nullptr, c->n_seq);
     run_match(c, c->d_cloud, pose_batch(c, pos_predict, pos_last), true);
     c->cloud_resident = true;
     CU(cudaMemcpyAsync(c->h_small, c->d_corr_total, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -663,8 +667,8 @@ extern "C" int nav_slam_mapping(nav_ctx *c, const nav_pos *pos, const nav_point 
     } else if (!c->cloud_resident) {
         return fail("nav_slam_mapping: cloud == NULL but no cloud is resident from a preceding match");
     }
-    run_map(c, c->d_cloud, pose_batch(c, pos, nullptr), true);
-    if (global_out && c->stage.d2h(global_out, c->d_global, c->ntot * 24, c->stream))
+    run_map(c, c->d_cloud, pose_batch(c, pos, nullptr));
+    if (global_out && c->stage.d2h(global_out, c->map.pts, c->ntot * 24, c->stream))
         return fail("nav_slam_mapping: D2H");
     return finish_call(c, "nav_slam_mapping");
 }
@@ -677,14 +681,13 @@ extern "C" int nav_frontend_frame(nav_ctx *c, const nav_point *cloud, const nav_
     if (!c->have_map) return fail("nav_frontend_frame: call nav_slam_init first");
     if (c->stage.reserve(c->ntot * (24 + 24 + 4 + 4 + 8) + 4096, c->stream)) return fail("nav_frontend_frame: staging");
     if (upload_cloud(c, cloud, "nav_frontend_frame")) return 1;
-    run_labels(c, c->d_cloud, c->d_labels, nullptr, c->n_seq);
     run_match(c, c->d_cloud, pose_batch(c, pos_predict, pos_last), false);
-    run_map(c, c->d_cloud, pose_batch(c, pos_final, nullptr), true);
+    run_map(c, c->d_cloud, pose_batch(c, pos_final, nullptr));
     c->cloud_resident = true;
     if (feature_out && c->stage.d2h(feature_out, c->d_labels, c->ntot * 4, c->stream)) return fail("nav_frontend_frame: D2H");
     if (nn_idx_out && c->stage.d2h(nn_idx_out, c->d_nn_idx, c->ntot * 4, c->stream)) return fail("nav_frontend_frame: D2H");
     if (nn_dist_out && c->stage.d2h(nn_dist_out, c->d_nn_dist, c->ntot * 8, c->stream)) return fail("nav_frontend_frame: D2H");
-    if (global_out && c->stage.d2h(global_out, c->d_global, c->ntot * 24, c->stream)) return fail("nav_frontend_frame: D2H");
+    if (global_out && c->stage.d2h(global_out, c->map.pts, c->ntot * 24, c->stream)) return fail("nav_frontend_frame: D2H");
     return finish_call(c, "nav_frontend_frame");
 }
 
@@ -703,9 +706,8 @@ extern "C" int nav_frontend_frame_dev(nav_ctx *c, const void *dev_cloud, const n
     if (!dev_cloud || !pos_predict || !pos_last || !pos_final) return fail("nav_frontend_frame_dev: null argument");
     if (!c->have_map) return fail("nav_frontend_frame_dev: call nav_slam_init_dev first");
     const double *cl = (const double *)dev_cloud;
-    run_labels(c, cl, c->d_labels, nullptr, c->n_seq);
     run_match(c, cl, pose_batch(c, pos_predict, pos_last), false);
-    run_map(c, cl, pose_batch(c, pos_final, nullptr), true);
+    run_map(c, cl, pose_batch(c, pos_final, nullptr));
     c->cloud_resident = false;
     CU(cudaGetLastError());
     return 0;
@@ -716,8 +718,8 @@ extern "C" int nav_frame_results_dev(nav_ctx *c, nav_frame_results *out) {
     out->labels = c->d_labels;
     out->nn_idx = c->d_nn_idx;
     out->nn_dist = c->d_nn_dist;
-    out->global = c->d_global;
-    out->map_count = c->map.count;
+    out->global = c->map.pts;
+    out->map_mask = c->map.mask;
     return 0;
 }
 
@@ -725,16 +727,32 @@ extern "C" int nav_row_map_export(nav_ctx *c, int seq, int row, nav_point *pts_o
     CTX_ENTER(c, "nav_row_map_export");
     if (!pts_out || !n_out) return fail("nav_row_map_export: null argument");
     if (seq < 0 || seq >= c->n_seq || row < 0 || row >= c->rows) return fail("nav_row_map_export: bad row");
+    *n_out = 0;
+    if (!c->have_map) return 0;
+    const size_t rid = (size_t)seq * c->rows + row, cols = c->cols;
+    double *d_out = c->d_flat + cols * 3;
+    int *d_col = (int *)(c->d_flat + cols * 6) + cols;
+    launch_flatten_row(c->map.pts + rid * cols * 3, nullptr, c->map.mask + rid * c->map.n_chunks, d_out, d_col,
+                       c->d_flat_count, c->cols, c->stream);
+    c->launches++;
     CU(cudaStreamSynchronize(c->stream));
-    const size_t rid = (size_t)seq * c->rows + row;
     int n = 0;
-    if (c->have_map) CU(cudaMemcpy(&n, c->map.count + rid, 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&n, c->d_flat_count, 4, cudaMemcpyDeviceToHost));
     if (n > 0) {
-        CU(cudaMemcpy(pts_out, c->map.pts + rid * c->cols * 3, (size_t)n * 24, cudaMemcpyDeviceToHost));
-        if (col_out) CU(cudaMemcpy(col_out, c->map.col + rid * c->cols, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(pts_out, d_out, (size_t)n * 24, cudaMemcpyDeviceToHost));
+        if (col_out) CU(cudaMemcpy(col_out, d_col, (size_t)n * 4, cudaMemcpyDeviceToHost));
     }
     *n_out = (size_t)n;
     return 0;
+}
+
+extern "C" uint64_t nav_exact_fallback_count(nav_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    unsigned v = 0;
+    cudaStreamSynchronize(c->stream);
+    cudaMemcpy(&v, c->d_n_exact, 4, cudaMemcpyDeviceToHost);
+    return v;
 }
 
 // ------------------------------------------------------------------ kd-tree ------------------
@@ -776,6 +794,13 @@ static nav_kdtree *kd_new(int device, size_t n) {
         return nullptr;
     }
     CUP(cudaSetDevice(device));
+    {   // the build takes its workspace from the stream-ordered pool: keep freed blocks cached
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     nav_kdtree *t = new nav_kdtree();
     t->device = device;
     t->n = n;

@@ -13,85 +13,60 @@
 // exactly as src/slam.c:37-58 does.  That halves the fp64 square roots (2 per point, not 4; the
 // reference evaluates 8).  Algorithmic traffic: 24 B read + 4 B written per point.
 #include "nav_kernels.cuh"
+#include "stencil_tile.cuh"
 
 namespace nav {
 
-constexpr int kTile = 256;
-constexpr int kHalo = 2;
-
-template <bool kWriteCurv>
+// labels for n_rows image rows (any number of images back to back): persistent grid-stride loop
+// over (row, 256-column tile) pairs, fp32-filtered evaluation with exact fallback (stencil_tile.cuh)
 __global__ void __launch_bounds__(kTile)
-k_labels_exact(const double *__restrict__ cloud, int *__restrict__ labels,
-               double *__restrict__ curv_out, long long n_rows, int cols, int tiles_per_row) {
-    __shared__ double s_pts[(kTile + 2 * kHalo) * 3];
-    __shared__ double s_f1[kTile + kHalo];
-    __shared__ double s_f2[kTile + kHalo];
-
+k_labels(const double *__restrict__ cloud, int *__restrict__ labels, long long n_rows, int cols,
+         int tiles_per_row, unsigned *__restrict__ n_exact) {
+    __shared__ StencilSmem s;
     const long long n_tiles = n_rows * tiles_per_row;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long row = tile / tiles_per_row;
         const int c0 = (int)(tile % tiles_per_row) * kTile;
-        const double *row_ptr = cloud + row * (long long)cols * 3;
-
-        // stage columns [c0-2, c0+kTile+2) clipped to the row; out-of-row slots are zero and only
-        // feed border columns, which the reference never evaluates (src/slam.c:16)
-        const int first = c0 - kHalo;
-        for (int i = threadIdx.x; i < (kTile + 2 * kHalo) * 3; i += kTile) {
-            int col = first + i / 3;
-            double v = 0.0;
-            if (col >= 0 && col < cols) v = __ldg(row_ptr + (long long)first * 3 + i);
-            s_pts[i] = v;
-        }
+        tile_stage(s, cloud + row * (long long)cols * 3, c0, cols);
         __syncthreads();
+        const int label = tile_labels_filtered(s, c0, cols, n_exact);
+        const int col = c0 + threadIdx.x;
+        if (col < cols) labels[row * (long long)cols + col] = label;
+    }
+}
 
-        for (int i = threadIdx.x; i < kTile + kHalo; i += kTile) {
-            const double *p = s_pts + i * 3;
-            s_f1[i] = __dsqrt_rn(dsq3(dsub(p[0], p[3]), dsub(p[1], p[4]), dsub(p[2], p[5])));
-            s_f2[i] = __dsqrt_rn(dsq3(dsub(p[0], p[6]), dsub(p[1], p[7]), dsub(p[2], p[8])));
-        }
+// exact binary64 curvature (test hook of the C ABI) and the labels derived from it
+__global__ void __launch_bounds__(kTile)
+k_curvature(const double *__restrict__ cloud, int *__restrict__ labels, double *__restrict__ curv_out,
+            long long n_rows, int cols, int tiles_per_row) {
+    __shared__ StencilSmem s;
+    const long long n_tiles = n_rows * tiles_per_row;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row = tile / tiles_per_row;
+        const int c0 = (int)(tile % tiles_per_row) * kTile;
+        tile_stage(s, cloud + row * (long long)cols * 3, c0, cols);
         __syncthreads();
-
+        const double curv = tile_curvature_exact(s, c0, cols);
         const int col = c0 + threadIdx.x;
         if (col < cols) {
-            const int li = threadIdx.x + kHalo;
-            double curv = 0.0;
-            if (col >= kHalo && col < cols - kHalo) {
-                const double dm2 = s_f2[li - 2], dm1 = s_f1[li - 1], dp1 = s_f1[li], dp2 = s_f2[li];
-                const double sum = dadd(dadd(dadd(dm2, dm1), dp1), dp2);
-                const double avg = dmul(sum, 0.25);  // sum / 4 is exact scaling
-                if (avg > 0.0) {
-                    double e = dsub(dm2, avg);
-                    double var = dmul(e, e);
-                    e = dsub(dm1, avg);
-                    var = dadd(var, dmul(e, e));
-                    e = dsub(dp1, avg);
-                    var = dadd(var, dmul(e, e));
-                    e = dsub(dp2, avg);
-                    var = dadd(var, dmul(e, e));
-                    curv = __ddiv_rn(dmul(var, 0.25), dadd(dmul(avg, avg), (double)1e-6f));
-                }
-            }
             const long long o = row * (long long)cols + col;
             labels[o] = curv > 0.1 ? 1 : 0;
-            if (kWriteCurv) curv_out[o] = curv;
+            curv_out[o] = curv;
         }
-        __syncthreads();
     }
 }
 
 void launch_labels(const double *cloud, int *labels, double *curv_or_null, long long n_rows, int cols,
-                   int sm_count, cudaStream_t stream) {
+                   int sm_count, unsigned *n_exact, cudaStream_t stream) {
     if (n_rows <= 0 || cols <= 0) return;
     const int tiles_per_row = div_up(cols, kTile);
     const long long n_tiles = n_rows * tiles_per_row;
     long long grid = (long long)sm_count * 8;
     if (grid > n_tiles) grid = n_tiles;
     if (curv_or_null)
-        k_labels_exact<true><<<(unsigned)grid, kTile, 0, stream>>>(cloud, labels, curv_or_null, n_rows, cols,
-                                                                  tiles_per_row);
+        k_curvature<<<(unsigned)grid, kTile, 0, stream>>>(cloud, labels, curv_or_null, n_rows, cols, tiles_per_row);
     else
-        k_labels_exact<false><<<(unsigned)grid, kTile, 0, stream>>>(cloud, labels, nullptr, n_rows, cols,
-                                                                   tiles_per_row);
+        k_labels<<<(unsigned)grid, kTile, 0, stream>>>(cloud, labels, n_rows, cols, tiles_per_row, n_exact);
 }
 
 // ---------------------------------------------------------------- a2 ------------------------

@@ -91,6 +91,17 @@ static void publish_rows(int s) {
     for (int r = 0; r < MAX_ROWS; ++r) g_slots[s].attr->kdtree_lastframe[r] = (KDNode *)&g_slots[s].rows[r];
 }
 
+/* layout probes for tests/test_abi.py (compared with the reference's own compiled sizeof/offsetof) */
+int navslam_abi_rows(void) { return MAX_ROWS; }
+int navslam_abi_cols(void) { return MAX_COLS; }
+size_t navslam_abi_sizeof_pointcloud(void) { return sizeof(PointCloud); }
+size_t navslam_abi_sizeof_slam_attr(void) { return sizeof(SLAM_attr); }
+size_t navslam_abi_sizeof_kdnode(void) { return sizeof(KDNode); }
+size_t navslam_abi_sizeof_neighbor_result(void) { return sizeof(NeighborResult); }
+size_t navslam_abi_offsetof_frame_count(void) { return offsetof(SLAM_attr, frameCount); }
+size_t navslam_abi_offsetof_trees(void) { return offsetof(SLAM_attr, kdtree_lastframe); }
+size_t navslam_abi_offsetof_error(void) { return offsetof(SLAM_attr, error); }
+
 /* ---------------------------------------------------------------- slam.h ---------------- */
 /* headers/slam.h:22, src/slam.c:134-175 */
 void init_slam(SLAM_attr *attr, Pos pos, PointCloud *lidarPointCloud) {
