@@ -31,8 +31,12 @@
 //      den32 = fma(avg32,avg32,1e-6f)               -> |den32-den| <= 26u den
 //      c32 = 0.25 * V32 * rcp(den32)                -> |c32-curv| <= 25u avg A/den + 40u curv + 1e-11
 //    The kernel uses 64u (avg32 A32 / den32) + 64u c32 + 1e-9, i.e. more than twice that.
-//    Guards: any |diff32| that is not in [1e-15, 1e15] (and not exactly 0), or NaN, poisons the
-//    distance with NaN, which sends the point to the exact path.
+//    Range: overflow (|diff| > 1.8e19) gives inf, then avg = inf, e = inf - inf = NaN and the point
+//    goes to the exact path, as does any NaN input.  Underflow (a squared difference below
+//    FLT_MIN, flushed by sqrt.approx.ftz) costs an ABSOLUTE error below 2e-19 in that distance;
+//    an absolute error eps in one d_k moves c by at most 2*3avg*eps/den <= 3000 eps (den >= 2e-3 avg),
+//    i.e. < 1e-15, far inside the 1e-9 slack.  avg32 == 0 means all four distances are below 1.1e-19,
+//    for which the reference's curvature is < 1e-30: label 0.
 #pragma once
 #include "nav_common.cuh"
 
@@ -41,8 +45,10 @@ namespace nav {
 constexpr int kTile = 256;  // columns per CTA tile (= 16 leaf blocks = 1 super block of the row map)
 constexpr int kHalo = 2;
 
+constexpr int kTilePts = kTile + 2 * kHalo;  // staged points per tile
+
 struct StencilSmem {
-    double pts[(kTile + 2 * kHalo) * 3];
+    double pts[kTilePts * 3];
     union {
         struct {
             double f1[kTile + kHalo];
@@ -86,8 +92,8 @@ __device__ __forceinline__ double curvature_from_taps(double dm2, double dm1, do
 }
 
 // exact distance between staged points a and b (local indices)
-__device__ __forceinline__ double tile_dist(const StencilSmem &s, int a, int b) {
-    const double *p = s.pts + a * 3, *q = s.pts + b * 3;
+__device__ __forceinline__ double tile_dist(const double *pts, int a, int b) {
+    const double *p = pts + a * 3, *q = pts + b * 3;
     return __dsqrt_rn(dsq3(dsub(p[0], q[0]), dsub(p[1], q[1]), dsub(p[2], q[2])));
 }
 
@@ -95,8 +101,8 @@ __device__ __forceinline__ double tile_dist(const StencilSmem &s, int a, int b) 
 // Contains two __syncthreads: call from all kTile threads.
 __device__ __forceinline__ double tile_curvature_exact(StencilSmem &s, int c0, int cols) {
     for (int i = threadIdx.x; i < kTile + kHalo; i += kTile) {
-        s.ex.f1[i] = tile_dist(s, i, i + 1);
-        s.ex.f2[i] = tile_dist(s, i, i + 2);
+        s.ex.f1[i] = tile_dist(s.pts, i, i + 1);
+        s.ex.f2[i] = tile_dist(s.pts, i, i + 2);
     }
     __syncthreads();
     const int col = c0 + threadIdx.x, li = threadIdx.x + kHalo;
@@ -109,7 +115,7 @@ __device__ __forceinline__ double tile_curvature_exact(StencilSmem &s, int c0, i
 
 __device__ __forceinline__ float sqrt_approx(float x) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -118,53 +124,59 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
-// fp32 forward distance with the range guard (NaN = "decide this one exactly")
-__device__ __forceinline__ float tile_dist32(const StencilSmem &s, int a, int b) {
-    const double *p = s.pts + a * 3, *q = s.pts + b * 3;
+// fp32 forward distance: differences in binary64, everything after in fp32
+__device__ __forceinline__ float tile_dist32(const double *pts, int a, int b) {
+    const double *p = pts + a * 3, *q = pts + b * 3;
     const float dx = (float)dsub(p[0], q[0]), dy = (float)dsub(p[1], q[1]), dz = (float)dsub(p[2], q[2]);
-    const float m = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
-    const float smallest = fminf(fminf(dx == 0.f ? 1.f : fabsf(dx), dy == 0.f ? 1.f : fabsf(dy)),
-                                 dz == 0.f ? 1.f : fabsf(dz));
-    const bool ok = (m <= 1e15f) && (smallest >= 1e-15f);  // false for NaN as well
-    const float d = sqrt_approx(__fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz)));
-    return ok ? d : __int_as_float(0x7fc00000);
+    return sqrt_approx(__fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz)));
+}
+
+// the reference's exact binary64 label of staged point li (rare path: kept out of line so that its
+// sqrt/div sequences do not inflate the register budget of the streaming kernels)
+static __device__ __noinline__ int label_exact_at(const double *pts, int li) {
+    const double curv = curvature_from_taps(tile_dist(pts, li, li - 2), tile_dist(pts, li, li - 1),
+                                            tile_dist(pts, li, li + 1), tile_dist(pts, li, li + 2));
+    return curv > 0.1 ? 1 : 0;
+}
+
+// decide one label from the four fp32 tap distances, falling back to the reference's binary64
+// expression (evaluated from the staged points around local index li) when fp32 cannot decide
+__device__ __forceinline__ int label_from_taps32(float dm2, float dm1, float dp1, float dp2, const double *pts,
+                                                 int li, unsigned *n_exact) {
+    const float avg = 0.25f * (((dm2 + dm1) + dp1) + dp2);
+    const float e0 = dm2 - avg, e1 = dm1 - avg, e2 = dp1 - avg, e3 = dp2 - avg;
+    const float var = __fmaf_rn(e3, e3, __fmaf_rn(e2, e2, __fmaf_rn(e1, e1, e0 * e0)));
+    const float a_sum = (fabsf(e0) + fabsf(e1)) + (fabsf(e2) + fabsf(e3)) + 3.1e-5f * avg;  // A >= sum|e_k|
+    const float rden = rcp_approx(__fmaf_rn(avg, avg, 1e-6f));
+    const float c32 = 0.25f * var * rden;
+    const float u64 = 64.f * 5.9604645e-8f;
+    const float err = __fmaf_rn(u64, avg * a_sum * rden, __fmaf_rn(u64, c32, 1e-9f));
+    if (avg == 0.f) return 0;
+    if (c32 - err > 0.1000001f) return 1;
+    if (c32 + err < 0.0999999f) return 0;
+    // too close to call in fp32 (or NaN/inf): the reference's own arithmetic
+    if (n_exact) atomicAdd(n_exact, 1u);
+    return label_exact_at(pts, li);
 }
 
 // label (0/1) of the thread's own column; needs tile_stage + __syncthreads before.
 // Contains two __syncthreads: call from all kTile threads.  *n_exact counts exact re-evaluations.
-__device__ __forceinline__ int tile_labels_filtered(StencilSmem &s, int c0, int cols, unsigned *n_exact) {
+__device__ __forceinline__ int tile_labels_filtered(const double *pts, float *f1, float *f2, int c0, int cols,
+                                                    unsigned *n_exact) {
     for (int i = threadIdx.x; i < kTile + kHalo; i += kTile) {
-        s.fl.f1[i] = tile_dist32(s, i, i + 1);
-        s.fl.f2[i] = tile_dist32(s, i, i + 2);
+        f1[i] = tile_dist32(pts, i, i + 1);
+        f2[i] = tile_dist32(pts, i, i + 2);
     }
     __syncthreads();
     const int col = c0 + threadIdx.x, li = threadIdx.x + kHalo;
     int label = 0;
-    if (col >= kHalo && col < cols - kHalo) {
-        const float dm2 = s.fl.f2[li - 2], dm1 = s.fl.f1[li - 1], dp1 = s.fl.f1[li], dp2 = s.fl.f2[li];
-        const float avg = 0.25f * (((dm2 + dm1) + dp1) + dp2);
-        const float e0 = dm2 - avg, e1 = dm1 - avg, e2 = dp1 - avg, e3 = dp2 - avg;
-        const float var = __fmaf_rn(e3, e3, __fmaf_rn(e2, e2, __fmaf_rn(e1, e1, e0 * e0)));
-        const float a_sum = (fabsf(e0) + fabsf(e1)) + (fabsf(e2) + fabsf(e3)) + 3.1e-5f * avg;  // A >= sum|e_k|
-        const float rden = rcp_approx(__fmaf_rn(avg, avg, 1e-6f));
-        const float c32 = 0.25f * var * rden;
-        const float u64 = 64.f * 5.9604645e-8f;
-        const float err = __fmaf_rn(u64, avg * a_sum * rden, __fmaf_rn(u64, c32, 1e-9f));
-        if (avg == 0.f) {
-            label = 0;  // all four distances are exactly zero (the guard excludes underflow): curv = 0
-        } else if (c32 - err > 0.1000001f) {
-            label = 1;
-        } else if (c32 + err < 0.0999999f) {
-            label = 0;
-        } else {  // too close to call in fp32 (or NaN/inf/out-of-range): the reference's own arithmetic
-            const double curv = curvature_from_taps(tile_dist(s, li, li - 2), tile_dist(s, li, li - 1),
-                                                    tile_dist(s, li, li + 1), tile_dist(s, li, li + 2));
-            label = curv > 0.1 ? 1 : 0;
-            if (n_exact) atomicAdd(n_exact, 1u);
-        }
-    }
+    if (col >= kHalo && col < cols - kHalo)
+        label = label_from_taps32(f2[li - 2], f1[li - 1], f1[li], f2[li], pts, li, n_exact);
     __syncthreads();
     return label;
+}
+__device__ __forceinline__ int tile_labels_filtered(StencilSmem &s, int c0, int cols, unsigned *n_exact) {
+    return tile_labels_filtered(s.pts, s.fl.f1, s.fl.f2, c0, cols, n_exact);
 }
 
 }  // namespace nav

@@ -95,11 +95,12 @@ def test_labels_near_threshold(ctxs, oracle):
     del base
 
 
-def test_labels_batch_dev(pkg, ctxs, oracle, synth):
+@pytest.mark.parametrize("shape,n", [((16, 1800), 5), ((64, 2048), 6), ((5, 33), 40), ((7, 300), 60)])
+def test_labels_batch_dev(pkg, ctxs, oracle, synth, shape, n):
+    """Batched labelling (TMA-fed kernel when the shape allows it, plain kernel otherwise)."""
     torch = pytest.importorskip("torch")
-    shape = (16, 1800)
     ctx = ctxs(shape)
-    frames = np.stack([_cloud(synth, shape, f) for f in range(5)])
+    frames = np.stack([_cloud(synth, shape, f, invalid_frac=0.01 if f % 3 == 0 else 0.0) for f in range(n)])
     d_clouds = torch.from_numpy(frames).cuda()
     d_labels = torch.empty(frames.shape[:-1], dtype=torch.int32, device="cuda")
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
