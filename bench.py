@@ -261,15 +261,31 @@ def run_gpu_arm(args):
     def frame_ptr(t, f):
         return t.data_ptr() + (f % n_frames) * NPX * 24
 
-    def dev_step(f):
-        pred, last, final = poses_for(f)
-        ctx.frontend_frame_dev(frame_ptr(d_frames, f), pred, last, final)
+    # ctypes pose structs are built once: the timed loops only make the C-ABI call
+    pose_c = {f: tuple(pa(p) for p in poses_for(f)) for f in range(0, K + 2 * W + 4)}
+    d_base, h_base = d_frames.data_ptr(), h_frames.data_ptr()
+    outs = [(h_feat.data_ptr(), h_idx.data_ptr(), h_dist.data_ptr(), h_glob.data_ptr())]
+    h_out2 = (torch.empty((ROWS, COLS), dtype=torch.int32).pin_memory(),
+              torch.empty((ROWS, COLS), dtype=torch.int32).pin_memory(),
+              torch.empty((ROWS, COLS), dtype=torch.float64).pin_memory(),
+              torch.empty((ROWS, COLS, 3), dtype=torch.float64).pin_memory())
+    outs.append(tuple(t.data_ptr() for t in h_out2))
 
-    def host_step(f):
-        pred, last, final = poses_for(f)
-        rc = L.nav_frontend_frame(ctx.h, frame_ptr(h_frames, f), pa(pred), pa(last), pa(final),
-                                  h_feat.data_ptr(), h_idx.data_ptr(), h_dist.data_ptr(), h_glob.data_ptr())
-        if rc:
+    def dev_step(f):
+        pp, pl, pf = pose_c[f]
+        if L.nav_frontend_frame_dev(ctx.h, d_base + (f % n_frames) * NPX * 24, pp, pl, pf):
+            raise RuntimeError(L.nav_last_error().decode())
+
+    def host_step(f):          # blocking call: returns with the results on the host
+        pp, pl, pf = pose_c[f]
+        o = outs[0]
+        if L.nav_frontend_frame(ctx.h, h_base + (f % n_frames) * NPX * 24, pp, pl, pf, o[0], o[1], o[2], o[3]):
+            raise RuntimeError(L.nav_last_error().decode())
+
+    def host_step_async(f):    # pipelined call: upload / kernels / download of neighbouring frames overlap
+        pp, pl, pf = pose_c[f]
+        o = outs[f & 1]
+        if L.nav_frontend_frame_async(ctx.h, h_base + (f % n_frames) * NPX * 24, pp, pl, pf, o[0], o[1], o[2], o[3]):
             raise RuntimeError(L.nav_last_error().decode())
 
     def barrier():
@@ -278,10 +294,12 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, first_frame):
+    def timed(step_fn, first_frame, drain=None):
         ctx.slam_init_dev(frame_ptr(d_frames, first_frame - 1), poses_for(first_frame - 1)[2])
         for i in range(W):
             step_fn(first_frame + i)
+        if drain:
+            drain()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launch_count()
@@ -289,6 +307,8 @@ def run_gpu_arm(args):
         t0 = time.perf_counter()
         for i in range(K):
             step_fn(first_frame + W + i)
+        if drain:
+            drain()
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
@@ -313,6 +333,11 @@ def run_gpu_arm(args):
     ctx.profile_enable(False)
     # --- e2e: host buffers in, host buffers out (the host call synchronises, so wall == device)
     e2e_ms, e2e_wall, _ = timed(host_step, 1)
+    # --- e2e, pipelined: same copies, overlapped across frames (wall clock: three streams are involved)
+    _, pipe_wall, _ = timed(host_step_async, 1, drain=ctx.frontend_wait)
+    pipe_ms = pipe_wall * 1e3
+    if world > 1:
+        pass  # timed() already reduced the wall time with MAX over ranks
     clk = clocks.stop()
 
     # --- dominant kernel roofline (SURVEY 8d algorithmic bytes)
@@ -391,7 +416,8 @@ def run_gpu_arm(args):
 
     if rank == 0:
         value = world * K / (dev_ms * 1e-3)
-        e2e = world * K / (e2e_ms * 1e-3)
+        e2e_blocking = world * K / (e2e_ms * 1e-3)
+        e2e = world * K / (pipe_ms * 1e-3)
         line = {
             "metric": "frames/sec (feature extract + NN match)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
@@ -402,8 +428,12 @@ def run_gpu_arm(args):
                        "l2_policy": "every step reads a different 3.1 MB frame of a %.2f GB resident sequence "
                                     "(> 126 MB L2); the previous frame's row maps (2 MB) are legitimately L2-warm"
                                     % (n_frames * NPX * 24 / 1e9)},
-            "e2e": {"value": e2e, "unit": "frames/s", "ms_per_step": e2e_ms / K, "wall_ms_per_step": 1e3 * e2e_wall / K,
-                    "h2d_bytes_per_step": NPX * 24, "d2h_bytes_per_step": NPX * (4 + 4 + 8 + 24)},
+            "e2e": {"value": e2e, "unit": "frames/s", "api": "nav_frontend_frame_async + nav_frontend_wait (pinned host "
+                    "buffers; upload, kernels and download of consecutive frames overlap)",
+                    "wall_ms_per_step": pipe_ms / K, "h2d_bytes_per_step": NPX * 24,
+                    "d2h_bytes_per_step": NPX * (4 + 4 + 8 + 24),
+                    "blocking_call": {"value": e2e_blocking, "unit": "frames/s", "api": "nav_frontend_frame",
+                                      "ms_per_step": e2e_ms / K, "wall_ms_per_step": 1e3 * e2e_wall / K}},
             "gpu_launches": launches, "clocks": clk,
             "roofline": None if dom is None else {
                 "kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,

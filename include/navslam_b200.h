@@ -126,6 +126,16 @@ int nav_frontend_frame(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos_
                        const nav_pos *pos_last, const nav_pos *pos_final, int *feature_out,
                        int32_t *nn_idx_out, double *nn_dist_out, nav_point *global_out);
 
+/* Pipelined variant of nav_frontend_frame for streams of frames: returns immediately; the upload of
+ * this frame, the kernels of the previous one and the downloads of the one before overlap on three
+ * CUDA streams.  All host pointers must be pinned (nav_host_alloc / cudaHostRegister).  The outputs
+ * of a frame are complete after nav_frontend_wait(), or once two further frames have been queued
+ * (use distinct output buffers for consecutive frames). */
+int nav_frontend_frame_async(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos_predict,
+                             const nav_pos *pos_last, const nav_pos *pos_final, int *feature_out,
+                             int32_t *nn_idx_out, double *nn_dist_out, nav_point *global_out);
+int nav_frontend_wait(nav_ctx *ctx);
+
 /* ---- device-resident entry points (inputs already in HBM) ------------------------------ */
 /* labels for n_images images [n_images][rows][cols] in one launch (pose independent) */
 int nav_extract_feature_batch_dev(nav_ctx *ctx, const void *dev_clouds, size_t n_images,

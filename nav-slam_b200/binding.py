@@ -43,7 +43,7 @@ EXPORTS = [
     "nav_slam_match", "nav_slam_localization", "nav_slam_mapping", "nav_frontend_frame",
     "nav_extract_feature_batch_dev", "nav_frontend_frame_dev", "nav_slam_init_dev",
     "nav_frame_results_dev", "nav_profile_enable", "nav_profile_read", "nav_row_map_export",
-    "nav_exact_fallback_count",
+    "nav_exact_fallback_count", "nav_frontend_frame_async", "nav_frontend_wait",
 ]
 
 
@@ -104,6 +104,9 @@ def load_library(build_if_missing: bool = True):
     L.nav_slam_mapping.argtypes = [vp, C.POINTER(NavPos), vp, vp]
     L.nav_frontend_frame.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
                                      vp, vp, vp, vp]
+    L.nav_frontend_frame_async.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
+                                           vp, vp, vp, vp]
+    L.nav_frontend_wait.argtypes = [vp]
     L.nav_extract_feature_batch_dev.argtypes = [vp, vp, C.c_size_t, vp]
     L.nav_frontend_frame_dev.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos)]
     L.nav_frame_results_dev.argtypes = [vp, C.POINTER(NavFrameResults)]
@@ -243,6 +246,17 @@ class Context:
                                          _pos_array(pos_last, n), _pos_array(pos_final, n), feat.ctypes.data,
                                          idx.ctypes.data, dist.ctypes.data, g.ctypes.data), self.L)
         return feat, idx, dist, g
+
+    def frontend_frame_async(self, cloud_ptr, pos_predict, pos_last, pos_final, feat_ptr, idx_ptr, dist_ptr,
+                             global_ptr):
+        """Pinned host pointers (ints); see nav_frontend_frame_async."""
+        n = self.n_seq
+        _check(self.L.nav_frontend_frame_async(self.h, cloud_ptr, _pos_array(pos_predict, n),
+                                               _pos_array(pos_last, n), _pos_array(pos_final, n), feat_ptr,
+                                               idx_ptr, dist_ptr, global_ptr), self.L)
+
+    def frontend_wait(self):
+        _check(self.L.nav_frontend_wait(self.h), self.L)
 
     # ---- device resident (raw device pointers, e.g. torch tensor .data_ptr())
     def set_stream(self, cuda_stream_handle):

@@ -174,6 +174,14 @@ struct nav_ctx {
     Stager stage;
     bool have_map = false, cloud_resident = false;
     uint64_t launches = 0;
+    // pipelined host path (nav_frontend_frame_async): two slots, copy-in / copy-out streams
+    struct AsyncSlot {
+        double *d_cloud = nullptr, *d_nn_dist = nullptr, *d_global = nullptr;
+        int *d_labels = nullptr, *d_nn_idx = nullptr;
+        cudaEvent_t in_done = nullptr, compute_done = nullptr, out_done = nullptr;
+    } slots[2];
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    uint64_t async_frames = 0;
     bool prof = false;
     ProfSlot prof_labels, prof_match, prof_map;
 };
@@ -251,6 +259,15 @@ extern "C" void nav_destroy(nav_ctx *c) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_small) cudaFreeHost(c->h_small);
+    for (auto &sl : c->slots) {
+        for (void *p : {(void *)sl.d_cloud, (void *)sl.d_nn_dist, (void *)sl.d_global, (void *)sl.d_labels,
+                        (void *)sl.d_nn_idx})
+            if (p) cudaFree(p);
+        for (cudaEvent_t e : {sl.in_done, sl.compute_done, sl.out_done})
+            if (e) cudaEventDestroy(e);
+    }
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
     c->stage.release();
     for (ProfSlot *s : {&c->prof_labels, &c->prof_match, &c->prof_map})
         for (auto &e : s->ev) {
@@ -314,8 +331,8 @@ extern "C" nav_ctx *nav_create(int rows, int cols, int device, int n_seq) {
     ALLOC(c->map.pts, nt * 24);
     ALLOC(c->map.mask, nr * c->map.n_chunks * 4);
     ALLOC(c->d_n_exact, 4);
-    ALLOC(c->map.box, nr * c->map.n_chunks * 48);
-    ALLOC(c->map.sbox, nr * c->map.n_super * 48);
+    ALLOC(c->map.box, nr * c->map.n_chunks * 32);
+    ALLOC(c->map.sbox, nr * c->map.n_super * 32);
     ALLOC(c->d_corr_rows, nt * sizeof(nav_corr));
     ALLOC(c->d_corr, nt * sizeof(nav_corr));
     ALLOC(c->d_corr_row_count, nr * 4);
@@ -689,6 +706,92 @@ extern "C" int nav_frontend_frame(nav_ctx *c, const nav_point *cloud, const nav_
     if (nn_dist_out && c->stage.d2h(nn_dist_out, c->d_nn_dist, c->ntot * 8, c->stream)) return fail("nav_frontend_frame: D2H");
     if (global_out && c->stage.d2h(global_out, c->map.pts, c->ntot * 24, c->stream)) return fail("nav_frontend_frame: D2H");
     return finish_call(c, "nav_frontend_frame");
+}
+
+// ------------------------------------------------------------------ pipelined host path ------
+// Same work as nav_frontend_frame, but nothing blocks: frame t's upload (copy-in stream), frame
+// t-1's kernels (context stream) and frame t-2's downloads (copy-out stream) overlap, with two
+// device slots for the per-frame buffers.  All host pointers must be pinned.  Outputs of frame t
+// are valid after nav_frontend_wait() (or after two further async calls).
+static int async_setup(nav_ctx *c) {
+    if (c->s_in) return 0;
+    CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (auto &sl : c->slots) {
+        CU(cudaMalloc((void **)&sl.d_cloud, c->ntot * 24));
+        CU(cudaMalloc((void **)&sl.d_global, c->ntot * 24));
+        CU(cudaMalloc((void **)&sl.d_nn_dist, c->ntot * 8));
+        CU(cudaMalloc((void **)&sl.d_labels, c->ntot * 4));
+        CU(cudaMalloc((void **)&sl.d_nn_idx, c->ntot * 4));
+        CU(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+extern "C" int nav_frontend_frame_async(nav_ctx *c, const nav_point *cloud, const nav_pos *pos_predict,
+                                        const nav_pos *pos_last, const nav_pos *pos_final, int *feature_out,
+                                        int32_t *nn_idx_out, double *nn_dist_out, nav_point *global_out) {
+    CTX_ENTER(c, "nav_frontend_frame_async");
+    if (!cloud || !pos_predict || !pos_last || !pos_final) return fail("nav_frontend_frame_async: null argument");
+    if (!c->have_map) return fail("nav_frontend_frame_async: call nav_slam_init first");
+    if (async_setup(c)) return 1;
+    const void *hp[] = {cloud, feature_out, nn_idx_out, nn_dist_out, global_out};
+    for (const void *p : hp)
+        if (p && !Stager::is_pinned(p))
+            return fail("nav_frontend_frame_async: host buffers must be pinned (nav_host_alloc / cudaHostRegister)");
+    nav_ctx::AsyncSlot &sl = c->slots[c->async_frames & 1];
+    const bool reused = c->async_frames >= 2;
+    // copy-in: the slot's cloud was last read by the kernels of frame t-2
+    if (reused) CU(cudaStreamWaitEvent(c->s_in, sl.compute_done, 0));
+    CU(cudaMemcpyAsync(sl.d_cloud, cloud, c->ntot * 24, cudaMemcpyHostToDevice, c->s_in));
+    CU(cudaEventRecord(sl.in_done, c->s_in));
+    // kernels: need the upload, and the slot's output buffers released by the downloads of frame t-2
+    CU(cudaStreamWaitEvent(c->stream, sl.in_done, 0));
+    if (reused) CU(cudaStreamWaitEvent(c->stream, sl.out_done, 0));
+    {
+        MatchOut out = {sl.d_nn_idx, sl.d_nn_dist, c->d_corr_rows, c->d_corr_row_count};
+        {
+            ProfScope ps(c, &c->prof_match);
+            launch_frame_match(sl.d_cloud, sl.d_labels, true, c->map, out, pose_batch(c, pos_predict, pos_last),
+                               c->n_seq, c->rows, c->cols, c->d_n_exact, c->stream);
+        }
+        {
+            ProfScope ps(c, &c->prof_map);
+            launch_frame_map(sl.d_cloud, sl.d_labels, c->map, pose_batch(c, pos_final, nullptr), c->n_seq, c->rows,
+                             c->cols, c->stream);
+        }
+        c->launches += 2;
+        // the mapped cloud is persistent state (next frame's map): hand the copy-out stream a snapshot
+        if (global_out)
+            CU(cudaMemcpyAsync(sl.d_global, c->map.pts, c->ntot * 24, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CU(cudaEventRecord(sl.compute_done, c->stream));
+    c->cloud_resident = false;
+    // copy-out
+    CU(cudaStreamWaitEvent(c->s_out, sl.compute_done, 0));
+    if (feature_out) CU(cudaMemcpyAsync(feature_out, sl.d_labels, c->ntot * 4, cudaMemcpyDeviceToHost, c->s_out));
+    if (nn_idx_out) CU(cudaMemcpyAsync(nn_idx_out, sl.d_nn_idx, c->ntot * 4, cudaMemcpyDeviceToHost, c->s_out));
+    if (nn_dist_out) CU(cudaMemcpyAsync(nn_dist_out, sl.d_nn_dist, c->ntot * 8, cudaMemcpyDeviceToHost, c->s_out));
+    if (global_out) CU(cudaMemcpyAsync(global_out, sl.d_global, c->ntot * 24, cudaMemcpyDeviceToHost, c->s_out));
+    CU(cudaEventRecord(sl.out_done, c->s_out));
+    c->async_frames++;
+    return 0;
+}
+
+extern "C" int nav_frontend_wait(nav_ctx *c) {
+    CTX_ENTER(c, "nav_frontend_wait");
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->s_out) CU(cudaStreamSynchronize(c->s_out));
+    if (c->s_in) CU(cudaStreamSynchronize(c->s_in));
+    // the synchronous entry points read labels from the context's own buffer: bring it up to date
+    if (c->async_frames) {
+        nav_ctx::AsyncSlot &sl = c->slots[(c->async_frames - 1) & 1];
+        CU(cudaMemcpyAsync(c->d_labels, sl.d_labels, c->ntot * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
 }
 
 // ------------------------------------------------------------------ device resident ----------

@@ -65,6 +65,33 @@ __device__ __forceinline__ double box_lower_bound(const double *__restrict__ box
     return dsq3(ex, ey, ez);
 }
 
+// The same bound with fp32 boxes: the box is stored rounded OUTWARD (lo down, hi up), the query is
+// bracketed by q_dn <= q <= q_up, and every operation rounds down, so
+//   ex <= the real per-axis gap <= |RN64(p - q)| for every point p of the box,
+// hence s = RD(ex^2+ey^2+ez^2) <= the real sum <= dsq3(...)/(1 - 2^-51); the final factor (1 - 2^-20)
+// makes the result STRICTLY smaller than any dsq the reference arithmetic can produce for that box.
+// Pruning "lb32 > float_round_up(best)" therefore never discards a candidate with dsq <= best.
+struct Q32 {
+    float dn[3], up[3];
+};
+__device__ __forceinline__ Q32 make_q32(const P3 &q) {
+    Q32 r;
+    r.dn[0] = __double2float_rd(q.x);
+    r.dn[1] = __double2float_rd(q.y);
+    r.dn[2] = __double2float_rd(q.z);
+    r.up[0] = __double2float_ru(q.x);
+    r.up[1] = __double2float_ru(q.y);
+    r.up[2] = __double2float_ru(q.z);
+    return r;
+}
+__device__ __forceinline__ float box_lower_bound32(const float4 lo, const float4 hi, const Q32 &q) {
+    const float ex = fmaxf(0.f, fmaxf(__fsub_rd(lo.x, q.up[0]), __fsub_rd(q.dn[0], hi.x)));
+    const float ey = fmaxf(0.f, fmaxf(__fsub_rd(lo.y, q.up[1]), __fsub_rd(q.dn[1], hi.y)));
+    const float ez = fmaxf(0.f, fmaxf(__fsub_rd(lo.z, q.up[2]), __fsub_rd(q.dn[2], hi.z)));
+    const float s = __fmaf_rd(ez, ez, __fmaf_rd(ey, ey, __fmul_rd(ex, ex)));
+    return __fmul_rd(s, 0.99999905f);
+}
+
 constexpr int kChunk = 16;       // map points per leaf box
 constexpr int kChunksPerSuper = 16;
 

@@ -19,8 +19,8 @@ void launch_transform(const double *in, double *out, long long n, const PoseXf &
 struct RowMap {
     double *pts;      // [n_seq*rows][cols][3]   global cloud of the frame mapped last
     unsigned *mask;   // [n_seq*rows][n_chunks]  bit i = column 16*b+i is an edge point
-    double *box;      // [n_seq*rows][n_chunks][6]   lo.xyz, hi.xyz (+inf/-inf when empty)
-    double *sbox;     // [n_seq*rows][n_super][6]
+    float4 *box;      // [n_seq*rows][n_chunks][2]   {lo.xyz,-}, {hi.xyz,-} rounded outward (+inf/-inf when empty)
+    float4 *sbox;     // [n_seq*rows][n_super][2]
     int n_chunks, n_super;
 };
 

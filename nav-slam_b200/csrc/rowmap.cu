@@ -64,7 +64,7 @@ __device__ __forceinline__ void half_minmax(double &lo, double &hi) {
 __global__ void __launch_bounds__(kTile)
 k_frame_map(const double *__restrict__ cloud, const int *__restrict__ labels, RowMap map,
             const __grid_constant__ PoseBatch poses, int rows, int cols, int tiles_per_row) {
-    __shared__ double s_box[kChunksPerSuper][6];
+    __shared__ float4 s_lo[kChunksPerSuper], s_hi[kChunksPerSuper];
     const int rid = blockIdx.x / tiles_per_row;  // sequence * rows + row
     const int tile = blockIdx.x % tiles_per_row;
     const int seq = rid / rows;
@@ -94,144 +94,39 @@ k_frame_map(const double *__restrict__ cloud, const int *__restrict__ labels, Ro
     for (int a = 0; a < 3; ++a) half_minmax(lo[a], hi[a]);
     const int leaf_in_tile = warp * 2 + half;
     const int leaf = tile * kChunksPerSuper + leaf_in_tile;
+    // boxes are stored in fp32 rounded outward (see box_lower_bound32)
+    const float4 flo = make_float4(__double2float_rd(lo[0]), __double2float_rd(lo[1]), __double2float_rd(lo[2]), 0.f);
+    const float4 fhi = make_float4(__double2float_ru(hi[0]), __double2float_ru(hi[1]), __double2float_ru(hi[2]), 0.f);
     if (l16 == 0) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            s_box[leaf_in_tile][a] = lo[a];
-            s_box[leaf_in_tile][3 + a] = hi[a];
-        }
+        s_lo[leaf_in_tile] = flo;
+        s_hi[leaf_in_tile] = fhi;
         if (leaf < map.n_chunks) {
             map.mask[(long long)rid * map.n_chunks + leaf] = mask16;
-            double *b = map.box + ((long long)rid * map.n_chunks + leaf) * 6;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                b[a] = lo[a];
-                b[3 + a] = hi[a];
-            }
+            float4 *b = map.box + ((long long)rid * map.n_chunks + leaf) * 2;
+            b[0] = flo;
+            b[1] = fhi;
         }
     }
     __syncthreads();
     if (warp == 0) {
-        double slo[3], shi[3];
+        float4 a = s_lo[l16], b = s_hi[l16];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            slo[a] = s_box[l16][a];
-            shi[a] = s_box[l16][3 + a];
-            half_minmax(slo[a], shi[a]);
+        for (int d = 8; d >= 1; d >>= 1) {
+            a.x = fminf(a.x, __shfl_xor_sync(kFull, a.x, d, 16));
+            a.y = fminf(a.y, __shfl_xor_sync(kFull, a.y, d, 16));
+            a.z = fminf(a.z, __shfl_xor_sync(kFull, a.z, d, 16));
+            b.x = fmaxf(b.x, __shfl_xor_sync(kFull, b.x, d, 16));
+            b.y = fmaxf(b.y, __shfl_xor_sync(kFull, b.y, d, 16));
+            b.z = fmaxf(b.z, __shfl_xor_sync(kFull, b.z, d, 16));
         }
         if (lane == 0) {
-            double *b = map.sbox + ((long long)rid * map.n_super + tile) * 6;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                b[a] = slo[a];
-                b[3 + a] = shi[a];
-            }
+            float4 *o = map.sbox + ((long long)rid * map.n_super + tile) * 2;
+            o[0] = a;
+            o[1] = b;
         }
     }
 }
 
-// scan the labelled points of one 16-column block of the map row
-__device__ __forceinline__ void scan_leaf(const double *__restrict__ row_pts, unsigned mask, int col0, const P3 &q,
-                                          double &best, int &bcol) {
-    while (mask) {
-        const int b = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int col = col0 + b;
-        const double *p = row_pts + (long long)col * 3;
-        // operand order of euclideanDistance(root->point, *target), utils/kdtree.c:116
-        const double d = dsq3(dsub(__ldg(p), q.x), dsub(__ldg(p + 1), q.y), dsub(__ldg(p + 2), q.z));
-        if (d < best || (d == best && col < bcol)) {
-            best = d;
-            bcol = col;
-        }
-    }
-}
-
-// grid as k_frame_map.  kFusedLabels: compute the labels of the tile here (and store them);
-// otherwise read them from `labels`.
-template <bool kFusedLabels>
-__global__ void __launch_bounds__(kTile)
-k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap map, MatchOut out,
-              const __grid_constant__ PoseBatch poses, int rows, int cols, int tiles_per_row,
-              unsigned *__restrict__ n_exact) {
-    __shared__ StencilSmem s;
-    const int rid = blockIdx.x / tiles_per_row;
-    const int tile = blockIdx.x % tiles_per_row;
-    const int seq = rid / rows, row = rid % rows;
-    const long long base = (long long)rid * cols;
-    const int c0 = tile * kTile;
-    const int c = c0 + threadIdx.x;
-
-    int label;
-    P3 p;
-    if (kFusedLabels) {
-        tile_stage(s, cloud + base * 3, c0, cols);
-        __syncthreads();
-        label = tile_labels_filtered(s, c0, cols, n_exact);
-        const double *sp = s.pts + (threadIdx.x + kHalo) * 3;
-        p.x = sp[0];
-        p.y = sp[1];
-        p.z = sp[2];
-        if (c < cols) labels[base + c] = label;
-    } else {
-        label = c < cols ? labels[base + c] : 0;
-        if (c < cols) p = ldg_p3(cloud + (base + c) * 3);
-    }
-    if (c >= cols) return;
-    if (label != 1) {
-        out.nn_idx[base + c] = -1;
-        out.nn_dist[base + c] = -1.0;
-        return;
-    }
-    const PoseXf &pose = poses.p[seq];
-    const P3 q = shift_point(pose, xf_point(pose, p));
-
-    const double *m_pts = map.pts + base * 3;
-    const unsigned *m_mask = map.mask + (long long)rid * map.n_chunks;
-    const double *m_box = map.box + (long long)rid * map.n_chunks * 6;
-    const double *m_sbox = map.sbox + (long long)rid * map.n_super * 6;
-    const int n_leaf = map.n_chunks, n_sup = map.n_super;
-
-    double best = INFINITY;
-    int bcol = -1;
-    const int seed = c / kChunk;
-    scan_leaf(m_pts, __ldg(m_mask + seed), seed * kChunk, q, best, bcol);
-    for (int sc = 0; sc < n_sup; ++sc) {
-        double bb[6];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) bb[a] = __ldg(m_sbox + sc * 6 + a);
-        if (!(box_lower_bound(bb, q) <= best)) continue;
-        const int l1 = min(n_leaf, (sc + 1) * kChunksPerSuper);
-        for (int lf = sc * kChunksPerSuper; lf < l1; ++lf) {
-            if (lf == seed) continue;
-#pragma unroll
-            for (int a = 0; a < 6; ++a) bb[a] = __ldg(m_box + lf * 6 + a);
-            if (!(box_lower_bound(bb, q) <= best)) continue;
-            scan_leaf(m_pts, __ldg(m_mask + lf), lf * kChunk, q, best, bcol);
-        }
-    }
-    out.nn_idx[base + c] = bcol >= 0 ? row * cols + bcol : -1;
-    out.nn_dist[base + c] = bcol >= 0 ? __dsqrt_rn(best) : INFINITY;
-}
-
-void launch_frame_map(const double *cloud, const int *labels, const RowMap &map, const PoseBatch &poses,
-                      int n_seq, int rows, int cols, cudaStream_t stream) {
-    const int tiles = div_up(cols, kTile);
-    k_frame_map<<<n_seq * rows * tiles, kTile, 0, stream>>>(cloud, labels, map, poses, rows, cols, tiles);
-}
-
-void launch_frame_match(const double *cloud, int *labels, bool fused_labels, const RowMap &map,
-                        const MatchOut &out, const PoseBatch &poses, int n_seq, int rows, int cols,
-                        unsigned *n_exact, cudaStream_t stream) {
-    const int tiles = div_up(cols, kTile);
-    const int grid = n_seq * rows * tiles;
-    if (fused_labels)
-        k_frame_match<true><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles, n_exact);
-    else
-        k_frame_match<false><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles, n_exact);
-}
-
-// ---------------------------------------------------------------------------------------------
 // exclusive prefix of `pred` over the block (thread order), plus the block total
 __device__ __forceinline__ int block_excl_count(bool pred, int *s_warp, int &total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -257,6 +152,189 @@ __device__ __forceinline__ int block_excl_count(bool pred, int *s_warp, int &tot
     return s_warp[32 + warp] + in_warp;
 }
 
+// scan the labelled points of one 16-column block of the map row.  `pts` points at column col0 of
+// the block (shared-memory copy for the CTA's own neighbourhood, global memory otherwise).  Four
+// candidates are loaded before any arithmetic so that their load latencies overlap; a short last
+// group repeats its final candidate, which the lexicographic compare ignores.
+__device__ __forceinline__ void scan_leaf(const double *pts, unsigned mask, int col0, const P3 &q, double &best,
+                                          int &bcol) {
+    while (mask) {
+        int b[4];
+        b[0] = __ffs(mask) - 1;
+        mask &= mask - 1;
+#pragma unroll
+        for (int i = 1; i < 4; ++i) {
+            b[i] = mask ? __ffs(mask) - 1 : b[i - 1];
+            mask &= mask - 1;  // 0 & anything stays 0
+        }
+        double x[4], y[4], z[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double *p = pts + b[i] * 3;
+            x[i] = p[0];
+            y[i] = p[1];
+            z[i] = p[2];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            // operand order of euclideanDistance(root->point, *target), utils/kdtree.c:116
+            const double d = dsq3(dsub(x[i], q.x), dsub(y[i], q.y), dsub(z[i], q.z));
+            const int col = col0 + b[i];
+            if (d < best || (d == best && col < bcol)) {
+                best = d;
+                bcol = col;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// the CTA's neighbourhood of the row map, prefetched into shared memory while the labels are
+// computed: its own 256 columns plus one 16-column leaf on each side (almost every query finds its
+// neighbour there), and the super boxes of the whole row
+constexpr int kNbLeaves = kChunksPerSuper + 2;
+constexpr int kMaxSuperSmem = 64;  // rows wider than 64*256 columns read the super boxes from global memory
+struct MapSmem {
+    double pts[kNbLeaves * kChunk * 3];
+    float4 box[kNbLeaves * 2];
+    float4 sbox[kMaxSuperSmem * 2];
+    unsigned mask[kNbLeaves];
+};
+
+// grid as k_frame_map.  kFusedLabels: compute the labels of the tile here (and store them);
+// otherwise read them from `labels`.
+template <bool kFusedLabels>
+__global__ void __launch_bounds__(kTile)
+k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap map, MatchOut out,
+              const __grid_constant__ PoseBatch poses, int rows, int cols, int tiles_per_row,
+              unsigned *__restrict__ n_exact) {
+    __shared__ StencilSmem s;
+    const int rid = blockIdx.x / tiles_per_row;
+    const int tile = blockIdx.x % tiles_per_row;
+    const int seq = rid / rows, row = rid % rows;
+    const long long base = (long long)rid * cols;
+    const int c0 = tile * kTile;
+    const int c = c0 + threadIdx.x;
+
+    __shared__ int s_warp[65];
+    __shared__ int s_qcol[kTile];
+    __shared__ MapSmem sm;
+    const double *m_pts = map.pts + base * 3;
+    const unsigned *m_mask = map.mask + (long long)rid * map.n_chunks;
+    const float4 *m_box = map.box + (long long)rid * map.n_chunks * 2;
+    const float4 *m_sbox = map.sbox + (long long)rid * map.n_super * 2;
+    const int n_leaf = map.n_chunks, n_sup = map.n_super;
+    const int leaf0 = tile * kChunksPerSuper - 1;  // first leaf of the prefetched neighbourhood (may be -1)
+    {   // asynchronous prefetch (cp.async) of the neighbourhood; consumed after the label phase
+        const int col_lo = leaf0 * kChunk;
+        for (int i = threadIdx.x; i < kNbLeaves * kChunk * 3; i += kTile) {
+            const int col = col_lo + i / 3;
+            if (col >= 0 && col < cols) cp_async8(&sm.pts[i], m_pts + (long long)col_lo * 3 + i);
+        }
+        if (threadIdx.x < kNbLeaves * 2) {
+            const int lf = leaf0 + (int)threadIdx.x / 2;
+            if (lf >= 0 && lf < n_leaf) cp_async16(&sm.box[threadIdx.x], m_box + (long long)leaf0 * 2 + threadIdx.x);
+        } else if (threadIdx.x >= 64 && threadIdx.x < 64 + kNbLeaves) {
+            const int j = threadIdx.x - 64, lf = leaf0 + j;
+            sm.mask[j] = (lf >= 0 && lf < n_leaf) ? __ldg(m_mask + lf) : 0u;
+        } else if (threadIdx.x >= 128 && (int)threadIdx.x < 128 + 2 * min(n_sup, kMaxSuperSmem)) {
+            cp_async16(&sm.sbox[threadIdx.x - 128], m_sbox + (threadIdx.x - 128));
+        }
+    }
+    int label;
+    if (kFusedLabels) {
+        tile_stage(s, cloud + base * 3, c0, cols);
+        __syncthreads();
+        label = tile_labels_filtered(s, c0, cols, n_exact);
+        if (c < cols) labels[base + c] = label;
+    } else {
+        label = c < cols ? labels[base + c] : 0;
+    }
+    if (c < cols && label != 1) {
+        out.nn_idx[base + c] = -1;
+        out.nn_dist[base + c] = -1.0;
+    }
+    // compact the labelled columns of the tile so that the search runs on densely populated warps
+    cp_async_wait_all();
+    int nq;
+    const int slot = block_excl_count(label == 1, s_warp, nq);  // its barriers also publish the prefetch
+    if (label == 1) s_qcol[slot] = threadIdx.x;
+    __syncthreads();
+    if ((int)threadIdx.x >= nq) return;
+    const int t = s_qcol[threadIdx.x];  // column-in-tile handled by this thread
+    const int qc = c0 + t;
+    P3 p;
+    if (kFusedLabels) {
+        const double *sp = s.pts + (t + kHalo) * 3;
+        p.x = sp[0];
+        p.y = sp[1];
+        p.z = sp[2];
+    } else {
+        p = ldg_p3(cloud + (base + qc) * 3);
+    }
+    const PoseXf &pose = poses.p[seq];
+    const P3 q = shift_point(pose, xf_point(pose, p));
+    const Q32 q32 = make_q32(q);
+    const bool sup_in_smem = n_sup <= kMaxSuperSmem;
+
+    double best = INFINITY;
+    float best_up = INFINITY;  // float(best) rounded up
+    int bcol = -1;
+    const int seed = qc / kChunk;
+    scan_leaf(sm.pts + (seed - leaf0) * kChunk * 3, sm.mask[seed - leaf0], seed * kChunk, q, best, bcol);
+    best_up = __double2float_ru(best);
+    for (int sc = 0; sc < n_sup; ++sc) {
+        const float4 slo = sup_in_smem ? sm.sbox[sc * 2] : __ldg(m_sbox + sc * 2);
+        const float4 shi = sup_in_smem ? sm.sbox[sc * 2 + 1] : __ldg(m_sbox + sc * 2 + 1);
+        if (box_lower_bound32(slo, shi, q32) > best_up) continue;
+        const int l1 = min(n_leaf, (sc + 1) * kChunksPerSuper);
+        for (int lf = sc * kChunksPerSuper; lf < l1; ++lf) {
+            if (lf == seed) continue;
+            const int j = lf - leaf0;
+            const bool near_leaf = j >= 0 && j < kNbLeaves;
+            const float4 blo = near_leaf ? sm.box[j * 2] : __ldg(m_box + lf * 2);
+            const float4 bhi = near_leaf ? sm.box[j * 2 + 1] : __ldg(m_box + lf * 2 + 1);
+            if (box_lower_bound32(blo, bhi, q32) > best_up) continue;
+            if (near_leaf)
+                scan_leaf(sm.pts + j * kChunk * 3, sm.mask[j], lf * kChunk, q, best, bcol);
+            else
+                scan_leaf(m_pts + (long long)lf * kChunk * 3, __ldg(m_mask + lf), lf * kChunk, q, best, bcol);
+            best_up = __double2float_ru(best);
+        }
+    }
+    out.nn_idx[base + qc] = bcol >= 0 ? row * cols + bcol : -1;
+    out.nn_dist[base + qc] = bcol >= 0 ? __dsqrt_rn(best) : INFINITY;
+}
+
+void launch_frame_map(const double *cloud, const int *labels, const RowMap &map, const PoseBatch &poses,
+                      int n_seq, int rows, int cols, cudaStream_t stream) {
+    const int tiles = div_up(cols, kTile);
+    k_frame_map<<<n_seq * rows * tiles, kTile, 0, stream>>>(cloud, labels, map, poses, rows, cols, tiles);
+}
+
+void launch_frame_match(const double *cloud, int *labels, bool fused_labels, const RowMap &map,
+                        const MatchOut &out, const PoseBatch &poses, int n_seq, int rows, int cols,
+                        unsigned *n_exact, cudaStream_t stream) {
+    const int tiles = div_up(cols, kTile);
+    const int grid = n_seq * rows * tiles;
+    if (fused_labels)
+        k_frame_match<true><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles, n_exact);
+    else
+        k_frame_match<false><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles, n_exact);
+}
+
+// ---------------------------------------------------------------------------------------------
 constexpr int kRowThreads = 512;
 
 // per-row dedupe, src/slam.c:247-283: one entry per matched map point; the query with the smallest

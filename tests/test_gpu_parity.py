@@ -226,6 +226,50 @@ def test_frontend_multi_sequence(pkg, oracle, synth):
         s.close()
 
 
+def test_frontend_async_pipeline_matches_sync(pkg, oracle, synth):
+    """nav_frontend_frame_async (three overlapping streams, two slots) returns what the blocking call
+    returns, frame for frame."""
+    torch = pytest.importorskip("torch")
+    shape, n = (16, 1800), 7
+    r, c = shape
+    ctx = pkg.Context(r, c, device=0)
+    slam = oracle.slam(r, c, 1)
+    clouds = torch.from_numpy(np.stack([synth.room_frame(r, c, f) for f in range(n)])).pin_memory()
+    feat = torch.empty((n, r, c), dtype=torch.int32).pin_memory()
+    idx = torch.empty((n, r, c), dtype=torch.int32).pin_memory()
+    dist = torch.empty((n, r, c), dtype=torch.float64).pin_memory()
+    glob = torch.empty((n, r, c, 3), dtype=torch.float64).pin_memory()
+    pos0 = np.zeros(6)
+    ctx.slam_init(pos0, clouds[0].numpy())
+    slam.init(pos0, clouds[0].numpy())
+    poses = []
+    last = pos0
+    for f in range(1, n):
+        pred = last + np.array([49.0, 1.0, 0.0, 0.0, 0.0, 0.2])
+        final = last + np.array([50.0, 0.0, 0.0, 0.0, 0.0, 0.0])
+        poses.append((pred, last, final))
+        ctx.frontend_frame_async(clouds[f].data_ptr(), pred, last, final, feat[f].data_ptr(), idx[f].data_ptr(),
+                                 dist[f].data_ptr(), glob[f].data_ptr())
+        last = final
+    ctx.frontend_wait()
+    for f in range(1, n):
+        pred, last, final = poses[f - 1]
+        ofeat, oidx, odist, og = slam.frontend_frame(clouds[f].numpy(), pred, last, final)
+        assert np.array_equal(feat[f].numpy(), ofeat) and np.array_equal(idx[f].numpy(), oidx)
+        assert np.array_equal(dist[f].numpy(), odist) and np.array_equal(glob[f].numpy(), og)
+    # the blocking API continues seamlessly from the pipelined state
+    pred, final = last + np.array([49.0, 0, 0, 0, 0, 0]), last + np.array([50.0, 0, 0, 0, 0, 0])
+    extra = synth.room_frame(r, c, n)
+    a = ctx.frontend_frame(extra, pred, last, final)
+    b = slam.frontend_frame(extra, pred, last, final)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    with pytest.raises(pkg.NavError):  # pageable memory is refused
+        ctx.frontend_frame_async(extra.ctypes.data, pred, last, final, None, None, None, None)
+    ctx.close()
+    slam.close()
+
+
 # ------------------------------------------------------------------ whole step (a8 + Adam) ---
 @pytest.mark.parametrize("shape,frames", [((8, 8), 8), ((5, 33), 6), ((16, 1800), 3), ((64, 2048), 2)])
 def test_slam_step_bit_exact(ctxs, oracle, synth, shape, frames):
