@@ -384,35 +384,57 @@ def run_gpu_arm(args):
                                "frac_of_hbm_peak": st_bytes / (st_ms * 1e-3) / 1e9 / peak,
                                "input_bytes": n_b * NPX * 24, "note": "input > L2 (126 MB) when images >= 43"}
 
-    # --- kd-tree path (config 4): 1 M-point map, 131 072 queries, device resident
+    # --- kd-tree path: config 4 (1 M-point map) at N=1, config 5b (10 M-point map, queries sharded
+    #     across ranks against a replicated tree, one all_gather) at N>1
     nn = None
     if not args.skip_kdtree:
-        pts = pkg.synth.map_points(1_000_000)
-        q = pkg.synth.map_queries(pts, 131072)
-        d_pts, d_q = torch.from_numpy(pts).cuda(), torch.from_numpy(q).cuda()
-        d_i = torch.empty(131072, dtype=torch.int32, device="cuda")
-        d_d = torch.empty(131072, dtype=torch.float64, device="cuda")
+        sharding = importlib.import_module("nav-slam_b200.sharding")
+        n_map = 10_000_000 if (world > 1 or args.big_map) else 1_000_000
+        nq = 131072
         s = stream.cuda_stream
+        d_pts = torch.empty((n_map, 3), dtype=torch.float64, device="cuda")
+        if rank == 0:
+            d_pts.copy_(torch.from_numpy(pkg.synth.map_points(n_map)))
+        sharding.broadcast_points(d_pts)                                   # NCCL broadcast (no-op at N=1)
+        sample = d_pts[:: max(n_map // 200000, 1)].cpu().numpy()          # queries derive from the map
+        q = pkg.synth.map_queries(sample, nq)
+        d_q = torch.from_numpy(q).cuda()
         e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-        tree = pkg.KdTree(dev_ptr=d_pts.data_ptr(), n=1_000_000, device=local, stream=s)
+        tree = pkg.KdTree(dev_ptr=d_pts.data_ptr(), n=n_map, device=local, stream=s)   # warm the allocator
         tree.close()
         torch.cuda.synchronize()
         e0.record(stream)
-        tree = pkg.KdTree(dev_ptr=d_pts.data_ptr(), n=1_000_000, device=local, stream=s)
+        tree = pkg.KdTree(dev_ptr=d_pts.data_ptr(), n=n_map, device=local, stream=s)
         e1.record(stream)
+
+        def nn_fn(qs):
+            m = int(qs.shape[0])
+            i = torch.empty(m, dtype=torch.int32, device="cuda")
+            d = torch.empty(m, dtype=torch.float64, device="cuda")
+            tree.nn_batch_dev(qs.data_ptr(), m, i.data_ptr(), d.data_ptr(), s)
+            return i, d
+
         for _ in range(3):
-            tree.nn_batch_dev(d_q.data_ptr(), 131072, d_i.data_ptr(), d_d.data_ptr(), s)
-        torch.cuda.synchronize()
+            sharding.sharded_nn(nn_fn, d_q)
+        barrier()
         e2.record(stream)
-        for _ in range(5):
-            tree.nn_batch_dev(d_q.data_ptr(), 131072, d_i.data_ptr(), d_d.data_ptr(), s)
+        reps = 5
+        for _ in range(reps):
+            idx_all, dist_all = sharding.sharded_nn(nn_fn, d_q)
         e3.record(stream)
-        torch.cuda.synchronize()
-        q_ms = e2.elapsed_time(e3) / 5
-        nn = {"map_points": 1_000_000, "queries": 131072, "build_ms": e0.elapsed_time(e1), "query_ms": q_ms,
-              "queries_per_s": 131072 / (q_ms * 1e-3),
-              "alg_bytes_per_launch": 131072 * 36, "achieved_gbs": 131072 * 36 / (q_ms * 1e-3) / 1e9}
+        barrier()
+        q_ms, b_ms = e2.elapsed_time(e3) / reps, e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([q_ms, b_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            q_ms, b_ms = float(t[0]), float(t[1])
+        nn = {"workload": ("cfg5b: 10 M-point map replicated, 131072 queries sharded over %d ranks + all_gather" % world)
+              if n_map > 1_000_000 else "cfg4: 1 M-point map, 131072 queries",
+              "map_points": n_map, "queries": nq, "build_ms": b_ms, "query_ms": q_ms,
+              "queries_per_s": nq / (q_ms * 1e-3), "matched": int((idx_all >= 0).sum()),
+              "alg_bytes_per_launch": nq * 36 // world, "achieved_gbs": nq * 36 / (q_ms * 1e-3) / 1e9}
         tree.close()
+        del d_pts
 
     if rank == 0:
         value = world * K / (dev_ms * 1e-3)
@@ -455,6 +477,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=60)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-kdtree", action="store_true")
+    ap.add_argument("--big-map", action="store_true", help="use the 10 M-point map at N=1 too")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -1,0 +1,94 @@
+"""Multi-GPU partitioning of the front end.
+
+The path shards in exactly two ways, both without touching the kernels:
+
+  * independent sequences (config 5a): sequence s runs on rank s % world; nothing is exchanged on
+    the data path (poses / CSVs are gathered by the host afterwards);
+  * large-map queries (config 5b): the map is replicated (rank 0 broadcasts the points, every
+    rank builds the same flat kd-tree -- the build is deterministic and takes milliseconds), the
+    query set is cut into `world` contiguous shards, and ONE all_gather of (idx:int32, dist:f64)
+    reassembles the answers on every rank.
+
+Per-row maps of the SLAM step (<= cols points) are never worth sharding.  One process per GPU;
+torch.distributed (NCCL over NVLink on GPUs, gloo on CPU for the tests) is only the plumbing.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence, Tuple
+
+import numpy as np
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi) of n items; the first n % world ranks get one item more."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} / world {world}")
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def assign_sequences(n_seq: int, world: int) -> List[List[int]]:
+    """Round-robin sequence -> rank assignment (config 5a); ranks may get an empty list."""
+    return [list(range(r, n_seq, world)) for r in range(world)]
+
+
+def max_shard(n: int, world: int) -> int:
+    return (n + world - 1) // world
+
+
+def sharded_nn(nn_fn: Callable, queries, *, group=None, device=None):
+    """Answer `queries` ([nq,3] float64 torch tensor, identical on every rank) with this rank
+    computing only its shard through nn_fn(q_shard) -> (idx int32 [m], dist float64 [m]) and one
+    all_gather putting the full (idx, dist) on every rank.  Works with any backend: the tensors
+    live on `device` (cuda for NCCL, cpu for gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    nq = int(queries.shape[0])
+    lo, hi = shard_bounds(nq, world, rank)
+    idx_s, dist_s = nn_fn(queries[lo:hi])
+    if world == 1:
+        return idx_s, dist_s
+    device = device if device is not None else queries.device
+    m = max_shard(nq, world)
+    # pack (dist, idx) into one padded float64 buffer so that a single collective moves both
+    buf = torch.zeros((m, 2), dtype=torch.float64, device=device)
+    buf[: hi - lo, 0] = dist_s.to(torch.float64)
+    buf[: hi - lo, 1] = idx_s.to(torch.float64)  # int32 is exact in float64
+    out = torch.empty((world, m, 2), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(out.view(world * m, 2), buf, group=group)
+    idx = torch.empty(nq, dtype=torch.int32, device=device)
+    dd = torch.empty(nq, dtype=torch.float64, device=device)
+    for r in range(world):
+        a, b = shard_bounds(nq, world, r)
+        dd[a:b] = out[r, : b - a, 0]
+        idx[a:b] = out[r, : b - a, 1].to(torch.int32)
+    return idx, dd
+
+
+def broadcast_points(points, *, src: int = 0, group=None):
+    """Replicate the map points (torch tensor [n,3] float64 on the collective's device)."""
+    import torch.distributed as dist
+
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(points, src=src, group=group)
+    return points
+
+
+def gather_sequence_results(local: Sequence[Tuple[int, np.ndarray]], world: int, *, group=None):
+    """Host-side gather of per-sequence results [(sequence id, array)] to every rank (config 5a:
+    poses per sequence).  Not on the data path; uses all_gather_object."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or world == 1:
+        return dict(local)
+    box = [None] * world
+    dist.all_gather_object(box, list(local), group=group)
+    merged = {}
+    for part in box:
+        for sid, arr in part:
+            merged[sid] = arr
+    return merged
