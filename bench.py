@@ -234,6 +234,9 @@ def run_gpu_arm(args):
     if rank == 0 and world == 1 and not args.skip_cpu:
         cpu = cpu_baseline_single_core(args.cpu_frames)  # forks: do it before CUDA is initialised
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     pkg = load_pkg()
@@ -384,6 +387,31 @@ def run_gpu_arm(args):
                                "frac_of_hbm_peak": st_bytes / (st_ms * 1e-3) / 1e9 / peak,
                                "input_bytes": n_b * NPX * 24, "note": "input > L2 (126 MB) when images >= 43"}
 
+    # --- config 5a shape on one GPU: 8 independent sequences side by side in every launch (n_seq = 8)
+    batched = None
+    if not args.skip_batched:
+        S, Fb = 8, min(n_frames // 8, 25)
+        ctx8 = pkg.Context(ROWS, COLS, device=local, n_seq=S)
+        ctx8.set_stream(stream.cuda_stream)
+        # sequence s uses frames s, s+8, s+16 ... of the resident set (distinct data per sequence)
+        d8 = d_frames[: S * Fb].reshape(Fb, S, ROWS, COLS, 3)
+        pp = np.stack([np.stack([poses_for(f + 1)[0]] * S) for f in range(Fb)])
+        pl = np.stack([np.stack([poses_for(f + 1)[1]] * S) for f in range(Fb)])
+        pf = np.stack([np.stack([poses_for(f + 1)[2]] * S) for f in range(Fb)])
+        ctx8.slam_init_dev(d8[0].data_ptr(), pf[0])
+        ctx8.frontend_sequence_dev(d8[1].data_ptr(), Fb - 1, pp[1:], pl[1:], pf[1:])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx8.slam_init_dev(d8[0].data_ptr(), pf[0])
+        e0.record(stream)
+        ctx8.frontend_sequence_dev(d8[1].data_ptr(), Fb - 1, pp[1:], pl[1:], pf[1:])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        b_ms = e0.elapsed_time(e1)
+        batched = {"n_seq": S, "frames": S * (Fb - 1), "ms": b_ms, "frames_per_s": S * (Fb - 1) / (b_ms * 1e-3),
+                   "note": "8 sequences per launch through nav_frontend_sequence_dev (device resident)"}
+        ctx8.close()
+
     # --- kd-tree path: config 4 (1 M-point map) at N=1, config 5b (10 M-point map, queries sharded
     #     across ranks against a replicated tree, one all_gather) at N>1
     nn = None
@@ -460,7 +488,7 @@ def run_gpu_arm(args):
             "roofline": None if dom is None else {
                 "kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": None},
-            "kernels": kernels, "nn": nn, "cpu_baseline": cpu,
+            "kernels": kernels, "batched_sequences": batched, "nn": nn, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
@@ -477,6 +505,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=60)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-kdtree", action="store_true")
+    ap.add_argument("--skip-batched", action="store_true")
     ap.add_argument("--big-map", action="store_true", help="use the 10 M-point map at N=1 too")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

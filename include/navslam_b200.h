@@ -145,6 +145,11 @@ int nav_extract_feature_batch_dev(nav_ctx *ctx, const void *dev_clouds, size_t n
 int nav_frontend_frame_dev(nav_ctx *ctx, const void *dev_cloud, const nav_pos *pos_predict,
                            const nav_pos *pos_last, const nav_pos *pos_final);
 int nav_slam_init_dev(nav_ctx *ctx, const void *dev_cloud, const nav_pos *pos);
+/* replay of a recorded sequence with known poses: n_frames consecutive frames (each n_seq images) at
+ * dev_frames, pose arrays of n_frames*n_seq entries; equivalent to n_frames nav_frontend_frame_dev
+ * calls (frame f is matched against frame f-1), issued from one host call */
+int nav_frontend_sequence_dev(nav_ctx *ctx, const void *dev_frames, size_t n_frames, const nav_pos *pos_predict,
+                              const nav_pos *pos_last, const nav_pos *pos_final);
 typedef struct {
     void *labels;   /* int32  [n_seq][rows][cols] */
     void *nn_idx;   /* int32  [n_seq][rows][cols] */

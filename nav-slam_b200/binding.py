@@ -44,6 +44,7 @@ EXPORTS = [
     "nav_extract_feature_batch_dev", "nav_frontend_frame_dev", "nav_slam_init_dev",
     "nav_frame_results_dev", "nav_profile_enable", "nav_profile_read", "nav_row_map_export",
     "nav_exact_fallback_count", "nav_frontend_frame_async", "nav_frontend_wait",
+    "nav_frontend_sequence_dev",
 ]
 
 
@@ -109,6 +110,8 @@ def load_library(build_if_missing: bool = True):
     L.nav_frontend_wait.argtypes = [vp]
     L.nav_extract_feature_batch_dev.argtypes = [vp, vp, C.c_size_t, vp]
     L.nav_frontend_frame_dev.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos)]
+    L.nav_frontend_sequence_dev.argtypes = [vp, vp, C.c_size_t, C.POINTER(NavPos), C.POINTER(NavPos),
+                                            C.POINTER(NavPos)]
     L.nav_frame_results_dev.argtypes = [vp, C.POINTER(NavFrameResults)]
     L.nav_row_map_export.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.POINTER(C.c_size_t)]
     L.nav_exact_fallback_count.restype = C.c_uint64
@@ -279,6 +282,11 @@ class Context:
         n = self.n_seq
         _check(self.L.nav_frontend_frame_dev(self.h, dev_cloud_ptr, _pos_array(pos_predict, n),
                                              _pos_array(pos_last, n), _pos_array(pos_final, n)), self.L)
+
+    def frontend_sequence_dev(self, dev_frames_ptr, n_frames, pos_predict, pos_last, pos_final):
+        n = n_frames * self.n_seq
+        _check(self.L.nav_frontend_sequence_dev(self.h, dev_frames_ptr, n_frames, _pos_array(pos_predict, n),
+                                                _pos_array(pos_last, n), _pos_array(pos_final, n)), self.L)
 
     def frame_results_dev(self) -> NavFrameResults:
         r = NavFrameResults()

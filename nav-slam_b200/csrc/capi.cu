@@ -816,6 +816,24 @@ extern "C" int nav_frontend_frame_dev(nav_ctx *c, const void *dev_cloud, const n
     return 0;
 }
 
+extern "C" int nav_frontend_sequence_dev(nav_ctx *c, const void *dev_frames, size_t n_frames,
+                                         const nav_pos *pos_predict, const nav_pos *pos_last,
+                                         const nav_pos *pos_final) {
+    CTX_ENTER(c, "nav_frontend_sequence_dev");
+    if (!dev_frames || !pos_predict || !pos_last || !pos_final) return fail("nav_frontend_sequence_dev: null argument");
+    if (!c->have_map) return fail("nav_frontend_sequence_dev: call nav_slam_init_dev first");
+    const double *base = (const double *)dev_frames;
+    for (size_t f = 0; f < n_frames; ++f) {
+        const double *cl = base + f * c->ntot * 3;
+        const size_t o = f * (size_t)c->n_seq;
+        run_match(c, cl, pose_batch(c, pos_predict + o, pos_last + o), false);
+        run_map(c, cl, pose_batch(c, pos_final + o, nullptr));
+    }
+    c->cloud_resident = false;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int nav_frame_results_dev(nav_ctx *c, nav_frame_results *out) {
     if (!c || !out) return fail("nav_frame_results_dev: null argument");
     out->labels = c->d_labels;

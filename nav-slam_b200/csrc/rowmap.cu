@@ -27,6 +27,7 @@
 //   k_export_row / k_flatten_row : stable row compaction (a4) for the API and the shim
 #include <limits.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "nav_kernels.cuh"
 #include "stencil_tile.cuh"
