@@ -297,7 +297,19 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    d_spin = torch.empty((min(n_frames, 64), ROWS, COLS), dtype=torch.int32, device="cuda")
+
+    def spin_up(seconds=0.25):
+        """Keep the GPU busy so that the SM clocks are at their loaded level when a timed region starts
+        (host-side input generation leaves the device idle for seconds)."""
+        t_end = time.perf_counter() + seconds
+        while time.perf_counter() < t_end:
+            for _ in range(20):
+                ctx.extract_feature_batch_dev(d_frames.data_ptr(), d_spin.shape[0], d_spin.data_ptr())
+            torch.cuda.synchronize()
+
     def timed(step_fn, first_frame, drain=None):
+        spin_up()
         ctx.slam_init_dev(frame_ptr(d_frames, first_frame - 1), poses_for(first_frame - 1)[2])
         for i in range(W):
             step_fn(first_frame + i)
@@ -332,7 +344,8 @@ def run_gpu_arm(args):
     for name in ("labels", "match", "map"):
         ctx.profile_read(name, reset=True)
     timed(dev_step, 1)
-    prof = {name: ctx.profile_read(name, reset=True) for name in ("labels", "match", "map")}
+    # (the stand-alone labels kernel is not on the frame path: a3 is fused into the match kernel)
+    prof = {name: ctx.profile_read(name, reset=True) for name in ("match", "map")}
     ctx.profile_enable(False)
     # --- e2e: host buffers in, host buffers out (the host call synchronises, so wall == device)
     e2e_ms, e2e_wall, _ = timed(host_step, 1)
@@ -371,6 +384,7 @@ def run_gpu_arm(args):
     # --- the stencil on a device-resident batch (north_star: >= 60 % of HBM peak)
     n_b = min(n_frames, 256)
     d_lab = torch.empty((n_b, ROWS, COLS), dtype=torch.int32, device="cuda")
+    spin_up()
     for _ in range(3):
         ctx.extract_feature_batch_dev(d_frames.data_ptr(), n_b, d_lab.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -398,6 +412,7 @@ def run_gpu_arm(args):
         pp = np.stack([np.stack([poses_for(f + 1)[0]] * S) for f in range(Fb)])
         pl = np.stack([np.stack([poses_for(f + 1)[1]] * S) for f in range(Fb)])
         pf = np.stack([np.stack([poses_for(f + 1)[2]] * S) for f in range(Fb)])
+        spin_up()
         ctx8.slam_init_dev(d8[0].data_ptr(), pf[0])
         ctx8.frontend_sequence_dev(d8[1].data_ptr(), Fb - 1, pp[1:], pl[1:], pf[1:])
         torch.cuda.synchronize()
@@ -430,7 +445,7 @@ def run_gpu_arm(args):
         e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
         tree = pkg.KdTree(dev_ptr=d_pts.data_ptr(), n=n_map, device=local, stream=s)   # warm the allocator
         tree.close()
-        torch.cuda.synchronize()
+        spin_up()
         e0.record(stream)
         tree = pkg.KdTree(dev_ptr=d_pts.data_ptr(), n=n_map, device=local, stream=s)
         e1.record(stream)
@@ -442,6 +457,7 @@ def run_gpu_arm(args):
             tree.nn_batch_dev(qs.data_ptr(), m, i.data_ptr(), d.data_ptr(), s)
             return i, d
 
+        spin_up()
         for _ in range(3):
             sharding.sharded_nn(nn_fn, d_q)
         barrier()

@@ -115,6 +115,12 @@ int nav_slam_match(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos_pred
  * translation-only Adam fit on the host.  verbose != 0 prints the reference's per-iteration lines. */
 int nav_slam_localization(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos_predict,
                           const nav_pos *pos_last, nav_pos *pos_out, double *error_out, int verbose);
+/* The same step with the fit driven by five sufficient statistics reduced on the device (N, sum r,
+ * sum |r|^2 with r = ori - nearest): nothing but 40 bytes comes back and each of the 200
+ * iterations is O(1).  Sums are formed in a different order than the reference's sequential loop, so
+ * the pose agrees with nav_slam_localization to rounding (about 1e-9 relative), not bit for bit. */
+int nav_slam_localization_fast(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos_predict,
+                               const nav_pos *pos_last, nav_pos *pos_out, double *error_out, size_t *n_corr_out);
 /* slam_mapping (src/slam.c:393): global_out = pose(cloud), per-row map for the next frame.
  * cloud == NULL reuses the cloud (and labels) of the preceding nav_slam_match/localization call. */
 int nav_slam_mapping(nav_ctx *ctx, const nav_pos *pos, const nav_point *cloud, nav_point *global_out);

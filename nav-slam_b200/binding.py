@@ -44,7 +44,7 @@ EXPORTS = [
     "nav_extract_feature_batch_dev", "nav_frontend_frame_dev", "nav_slam_init_dev",
     "nav_frame_results_dev", "nav_profile_enable", "nav_profile_read", "nav_row_map_export",
     "nav_exact_fallback_count", "nav_frontend_frame_async", "nav_frontend_wait",
-    "nav_frontend_sequence_dev",
+    "nav_frontend_sequence_dev", "nav_slam_localization_fast",
 ]
 
 
@@ -102,6 +102,8 @@ def load_library(build_if_missing: bool = True):
                                  C.POINTER(C.c_size_t)]
     L.nav_slam_localization.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
                                         c_double_p, C.c_int]
+    L.nav_slam_localization_fast.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
+                                             c_double_p, C.POINTER(C.c_size_t)]
     L.nav_slam_mapping.argtypes = [vp, C.POINTER(NavPos), vp, vp]
     L.nav_frontend_frame.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
                                      vp, vp, vp, vp]
@@ -225,6 +227,16 @@ class Context:
                                             _pos_array(pos_last), C.byref(out), C.byref(err),
                                             1 if verbose else 0), self.L)
         return np.array([out.x, out.y, out.z, out.roll, out.pitch, out.yaw]), err.value
+
+    def slam_localization_fast(self, cloud, pos_predict, pos_last):
+        cloud = _pts(cloud)
+        out = NavPos()
+        err = C.c_double(0)
+        n = C.c_size_t(0)
+        _check(self.L.nav_slam_localization_fast(self.h, cloud.ctypes.data, _pos_array(pos_predict),
+                                                 _pos_array(pos_last), C.byref(out), C.byref(err), C.byref(n)),
+               self.L)
+        return np.array([out.x, out.y, out.z, out.roll, out.pitch, out.yaw]), err.value, int(n.value)
 
     def slam_mapping(self, pos, cloud=None, want_global=True):
         shape = (self.rows, self.cols, 3) if self.n_seq == 1 else (self.n_seq, self.rows, self.cols, 3)

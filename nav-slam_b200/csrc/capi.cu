@@ -161,6 +161,7 @@ struct nav_ctx {
     size_t npx = 0, ntot = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     double *d_cloud = nullptr, *d_global = nullptr, *d_curv = nullptr, *d_nn_dist = nullptr;
+    double *d_stats = nullptr;      // [n_seq][5] sufficient statistics of the translation fit
     unsigned *d_n_exact = nullptr;  // labels the fp32 filter could not decide (exact re-evaluations)
     int *d_labels = nullptr, *d_nn_idx = nullptr;
     RowMap map = {};
@@ -253,7 +254,7 @@ extern "C" void nav_destroy(nav_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->d_cloud, c->d_global, c->d_curv, c->d_nn_dist, c->d_labels, c->d_nn_idx, c->map.pts,
-                    c->map.mask, c->d_n_exact, c->map.box, c->map.sbox, c->d_corr_rows, c->d_corr,
+                    c->map.mask, c->d_n_exact, c->d_stats, c->map.box, c->map.sbox, c->d_corr_rows, c->d_corr,
                     c->d_corr_row_count, c->d_corr_total, c->d_dist, c->d_tan_col, c->d_tan_row, c->d_flat,
                     c->d_flat_count};
     for (void *p : ptrs)
@@ -331,6 +332,7 @@ extern "C" nav_ctx *nav_create(int rows, int cols, int device, int n_seq) {
     ALLOC(c->map.pts, nt * 24);
     ALLOC(c->map.mask, nr * c->map.n_chunks * 4);
     ALLOC(c->d_n_exact, 4);
+    ALLOC(c->d_stats, (size_t)n_seq * 5 * 8);
     ALLOC(c->map.box, nr * c->map.n_chunks * 32);
     ALLOC(c->map.sbox, nr * c->map.n_super * 32);
     ALLOC(c->d_corr_rows, nt * sizeof(nav_corr));
@@ -670,6 +672,56 @@ extern "C" int nav_slam_localization(nav_ctx *c, const nav_point *cloud, const n
     pos_out->roll = pos_last->roll + transform[3];
     pos_out->pitch = pos_last->pitch + transform[4];
     pos_out->yaw = pos_last->yaw + transform[5];
+    return 0;
+}
+
+// slam_localization with the fit driven by five sufficient statistics reduced on the device
+// (SURVEY 8f #2): no correspondence list crosses PCIe and the 200 iterations are O(1) each.
+// Same update rule as src/slam.c:341-370; sums are formed in a different order than the
+// reference's sequential loop, so poses agree to rounding (about 1e-9 relative), not bit for bit.
+extern "C" int nav_slam_localization_fast(nav_ctx *c, const nav_point *cloud, const nav_pos *pos_predict,
+                                          const nav_pos *pos_last, nav_pos *pos_out, double *error_out,
+                                          size_t *n_corr_out) {
+    CTX_ENTER(c, "nav_slam_localization_fast");
+    if (!cloud || !pos_predict || !pos_last || !pos_out) return fail("nav_slam_localization_fast: null argument");
+    if (c->n_seq != 1) return fail("nav_slam_localization_fast: needs n_seq == 1");
+    if (!c->have_map) return fail("nav_slam_localization_fast: call nav_slam_init first");
+    if (c->stage.reserve(c->ntot * 24 + 1024, c->stream)) return fail("nav_slam_localization_fast: staging");
+    if (upload_cloud(c, cloud, "nav_slam_localization_fast")) return 1;
+    run_match(c, c->d_cloud, pose_batch(c, pos_predict, pos_last), true);
+    launch_corr_stats(c->d_corr, c->d_corr_total, c->d_stats, 1, c->rows, c->cols, c->sm_count, c->stream);
+    c->launches++;
+    c->cloud_resident = true;
+    double *h = (double *)c->h_small;
+    CU(cudaMemcpyAsync(h, c->d_stats, 40, cudaMemcpyDeviceToHost, c->stream));
+    if (finish_call(c, "nav_slam_localization_fast")) return 1;
+    const double N = h[0], S[3] = {h[1], h[2], h[3]}, Q = h[4];
+    double t[6] = {pos_predict->x - pos_last->x,       pos_predict->y - pos_last->y,
+                   pos_predict->z - pos_last->z,       pos_predict->roll - pos_last->roll,
+                   pos_predict->pitch - pos_last->pitch, pos_predict->yaw - pos_last->yaw};
+    const double lr = 0.1, tol = 1e-6, b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    double m[3] = {0, 0, 0}, v[3] = {0, 0, 0}, prev = 0, total = 0;
+    for (int iter = 0; iter < 200; ++iter) {
+        total = Q - 2.0 * (t[0] * S[0] + t[1] * S[1] + t[2] * S[2]) + N * (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+        if (N == 0) total = 0;
+        if (fabs(total - prev) < tol) break;
+        prev = total;
+        for (int j = 0; j < 3; ++j) {
+            const double g = N > 0 ? -(S[j] - N * t[j]) / N : 0.0;
+            m[j] = b1 * m[j] + (1 - b1) * g;
+            v[j] = b2 * v[j] + (1 - b2) * g * g;
+            const double mh = m[j] / (1 - pow(b1, iter + 1)), vh = v[j] / (1 - pow(b2, iter + 1));
+            t[j] -= lr * mh / (sqrt(vh) + eps);
+        }
+    }
+    if (error_out) *error_out = N > 0 ? sqrt(fmax(total, 0.0) / N) : 0.0;
+    if (n_corr_out) *n_corr_out = (size_t)N;
+    pos_out->x = pos_last->x + t[0];
+    pos_out->y = pos_last->y + t[1];
+    pos_out->z = pos_last->z + t[2];
+    pos_out->roll = pos_last->roll + t[3];
+    pos_out->pitch = pos_last->pitch + t[4];
+    pos_out->yaw = pos_last->yaw + t[5];
     return 0;
 }
 

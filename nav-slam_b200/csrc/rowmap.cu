@@ -451,6 +451,52 @@ void launch_gather_corr(const nav_corr *corr_rows, const int *corr_row_count, na
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sufficient statistics of the translation-only fit.  With r_i = ori_i - nearest_i
+// every iteration of src/slam.c:319-338 only needs N, sum r (3) and sum |r|^2:
+//   totalError(t) = sum|r|^2 - 2 t.sum r + N|t|^2,   gradient = -(sum r - N t)/N.
+// stats_out[0..4] = {N, sum rx, sum ry, sum rz, sum |r|^2} per sequence, accumulated with fp64
+// atomics (the summation order differs from the reference's sequential loop: tolerance parity).
+__global__ void __launch_bounds__(256)
+k_corr_stats(const nav_corr *__restrict__ corr, const int *__restrict__ corr_total, double *__restrict__ stats_out,
+             int rows, int cols) {
+    __shared__ double s_part[8][4];
+    const int seq = blockIdx.y;
+    const int n = corr_total[seq];
+    const nav_corr *list = corr + (long long)seq * rows * cols;
+    double a[4] = {0, 0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double rx = list[i].ori.x - list[i].nearest.x, ry = list[i].ori.y - list[i].nearest.y,
+                     rz = list[i].ori.z - list[i].nearest.z;
+        a[0] += rx;
+        a[1] += ry;
+        a[2] += rz;
+        a[3] += rx * rx + ry * ry + rz * rz;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) a[k] += __shfl_xor_sync(kFull, a[k], d);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_part[warp][k] = a[k];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0;
+        for (int w = 0; w < 8; ++w) t += s_part[w][threadIdx.x];
+        atomicAdd(&stats_out[seq * 5 + 1 + threadIdx.x], t);
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) stats_out[seq * 5] = (double)n;
+}
+
+void launch_corr_stats(const nav_corr *corr, const int *corr_total, double *stats_out, int n_seq, int rows, int cols,
+                       int sm_count, cudaStream_t stream) {
+    cudaMemsetAsync(stats_out, 0, sizeof(double) * 5 * n_seq, stream);
+    dim3 grid(sm_count, n_seq);
+    k_corr_stats<<<grid, 256, 0, stream>>>(corr, corr_total, stats_out, rows, cols);
+}
+
+// ---------------------------------------------------------------------------------------------
 // flattenPoints (src/slam.c:64-72): stable compaction of one row where feature == 1 (function-level
 // mirror), or where the map's label mask is set (k_export_row: the flattenedPoints array the
 // reference would hand to buildKDTree, src/slam.c:170-171)

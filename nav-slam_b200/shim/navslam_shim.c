@@ -126,8 +126,23 @@ Pos slam_localization(SLAM_attr *attr, PointCloud *lidarPointCloud, Pos pos_pred
     }
     Pos out;
     double err = 0.0;
-    if (nav_slam_localization(g_slots[s].ctx, (const nav_point *)&lidarPointCloud->ToF_position[0][0],
-                              (const nav_pos *)&pos_predict, (const nav_pos *)&pos_last, (nav_pos *)&out, &err, 1))
+    /* default: the reference's sequential Adam loop on the host (bit-identical poses and the same
+     * per-iteration stdout).  NAVSLAM_ADAM=stats: fit from five device-reduced sums (no 3.5 MB
+     * correspondence download, no 200 x N host loop; poses equal to ~1e-9 relative, no per-iteration
+     * lines). */
+    static int fast = -1;
+    if (fast < 0) {
+        const char *e = getenv("NAVSLAM_ADAM");
+        fast = e && strcmp(e, "stats") == 0;
+    }
+    if (fast) {
+        if (nav_slam_localization_fast(g_slots[s].ctx, (const nav_point *)&lidarPointCloud->ToF_position[0][0],
+                                       (const nav_pos *)&pos_predict, (const nav_pos *)&pos_last, (nav_pos *)&out,
+                                       &err, NULL))
+            die("slam_localization");
+    } else if (nav_slam_localization(g_slots[s].ctx, (const nav_point *)&lidarPointCloud->ToF_position[0][0],
+                                     (const nav_pos *)&pos_predict, (const nav_pos *)&pos_last, (nav_pos *)&out, &err,
+                                     1))
         die("slam_localization");
     attr->error = err;
     g_slots[s].last_cloud = &lidarPointCloud->ToF_position[0][0];

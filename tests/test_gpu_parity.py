@@ -299,6 +299,30 @@ def test_slam_step_bit_exact(ctxs, oracle, synth, shape, frames):
     slam.close()
 
 
+def test_localization_from_sufficient_statistics(ctxs, oracle, synth):
+    """the fit from five device-reduced sums agrees with the reference's sequential loop
+    to rounding (tolerance parity: the summation order differs)."""
+    shape = (64, 2048)
+    ctx = ctxs(shape)
+    slam = oracle.slam(*shape, 1)
+    clouds = [synth.room_frame(*shape, f) for f in range(3)]
+    pos = np.zeros(6)
+    ctx.slam_init(pos, clouds[0])
+    slam.init(pos, clouds[0])
+    last = pos
+    for f in (1, 2):
+        pred = last + np.array([46.0, 2.0, -1.0, 0.0, 0.0, 0.0])
+        p_fast, err_fast, n_fast = ctx.slam_localization_fast(clouds[f], pred, last)
+        p_or, corr, err_or, _ = slam.localize(clouds[f], pred, last)
+        assert n_fast == corr.shape[0]
+        assert np.allclose(p_fast, p_or, rtol=1e-9, atol=1e-6), p_fast - p_or
+        assert abs(err_fast - err_or) <= 1e-6 * max(1.0, err_or)
+        ctx.slam_mapping(p_or, None)
+        slam.map(p_or, clouds[f])
+        last = p_or
+    slam.close()
+
+
 # ------------------------------------------------------------------ kd-tree (a5 / a6) --------
 def _check_inorder(nodes, lo, hi, depth, bounds):
     """Recursive invariant check of the in-order layout: left keys <= node key <= right keys."""
