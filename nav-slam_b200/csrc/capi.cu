@@ -934,6 +934,7 @@ struct nav_kdtree {
     size_t n = 0;
     KdNode *d_nodes = nullptr;
     double *d_pts = nullptr;  // build input order, for nearest_out
+    double *d_bbox = nullptr; // lo.xyz, hi.xyz of the points (query ordering)
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
     // query scratch
@@ -946,7 +947,8 @@ extern "C" void nav_kdtree_free(nav_kdtree *t) {
     if (!t) return;
     cudaSetDevice(t->device);
     if (t->stream) cudaStreamSynchronize(t->stream);
-    for (void *p : {(void *)t->d_nodes, (void *)t->d_pts, (void *)t->d_q, (void *)t->d_dist, (void *)t->d_idx})
+    for (void *p : {(void *)t->d_nodes, (void *)t->d_pts, (void *)t->d_q, (void *)t->d_dist, (void *)t->d_idx,
+                    (void *)t->d_bbox})
         if (p) cudaFree(p);
     if (t->stream) cudaStreamDestroy(t->stream);
     delete t;
@@ -979,6 +981,7 @@ static nav_kdtree *kd_new(int device, size_t n) {
     t->n = n;
     cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void **)&t->d_bbox, 48) != cudaSuccess ||
         (n && (cudaMalloc((void **)&t->d_nodes, n * sizeof(KdNode)) != cudaSuccess ||
                cudaMalloc((void **)&t->d_pts, n * 24) != cudaSuccess))) {
         fail("nav_kdtree_build: device allocation for %zu points failed", n);
@@ -999,7 +1002,7 @@ extern "C" nav_kdtree *nav_kdtree_build_dev(int device, const void *dev_points, 
     cudaError_t e = cudaSuccess;
     if (n) {
         e = cudaMemcpyAsync(t->d_pts, dev_points, n * 24, cudaMemcpyDeviceToDevice, s);
-        if (e == cudaSuccess) e = kd_build(t->d_pts, n, t->d_nodes, t->sm_count, s, &t->launches);
+        if (e == cudaSuccess) e = kd_build(t->d_pts, n, t->d_nodes, t->d_bbox, t->sm_count, s, &t->launches);
     }
     if (e != cudaSuccess) {
         fail("nav_kdtree_build_dev: %s", cudaGetErrorString(e));
@@ -1019,7 +1022,7 @@ extern "C" nav_kdtree *nav_kdtree_build(int device, const nav_point *points, siz
     cudaError_t e = cudaSuccess;
     if (n) {
         e = cudaMemcpyAsync(t->d_pts, points, n * 24, cudaMemcpyHostToDevice, t->stream);
-        if (e == cudaSuccess) e = kd_build(t->d_pts, n, t->d_nodes, t->sm_count, t->stream, &t->launches);
+        if (e == cudaSuccess) e = kd_build(t->d_pts, n, t->d_nodes, t->d_bbox, t->sm_count, t->stream, &t->launches);
         if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
     }
     if (e != cudaSuccess) {
@@ -1052,7 +1055,8 @@ extern "C" int nav_kdtree_nn_batch_dev(nav_kdtree *t, const void *dev_queries, s
     if (nq && (!dev_queries || !dev_idx || !dev_dist)) return fail("nav_kdtree_nn_batch_dev: null argument");
     CU(cudaSetDevice(t->device));
     cudaStream_t s = (cudaStream_t)cuda_stream;  // 0 = legacy default stream
-    CU(kd_nn(t->d_nodes, t->n, (const double *)dev_queries, nq, (int *)dev_idx, (double *)dev_dist, s, &t->launches));
+    CU(kd_nn(t->d_nodes, t->n, t->d_bbox, (const double *)dev_queries, nq, (int *)dev_idx, (double *)dev_dist,
+             t->sm_count, s, &t->launches));
     return 0;
 }
 
@@ -1074,7 +1078,7 @@ extern "C" int nav_kdtree_nn_batch(nav_kdtree *t, const nav_point *queries, size
         t->q_cap = nq;
     }
     CU(cudaMemcpyAsync(t->d_q, queries, nq * 24, cudaMemcpyHostToDevice, t->stream));
-    CU(kd_nn(t->d_nodes, t->n, t->d_q, nq, t->d_idx, t->d_dist, t->stream, &t->launches));
+    CU(kd_nn(t->d_nodes, t->n, t->d_bbox, t->d_q, nq, t->d_idx, t->d_dist, t->sm_count, t->stream, &t->launches));
     CU(cudaMemcpyAsync(idx_out, t->d_idx, nq * 4, cudaMemcpyDeviceToHost, t->stream));
     CU(cudaMemcpyAsync(dist_out, t->d_dist, nq * 8, cudaMemcpyDeviceToHost, t->stream));
     if (nearest_out && t->n) {

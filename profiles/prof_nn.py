@@ -36,6 +36,17 @@ def timed(fn, reps=5):
 for n in sizes:
     pts = nav.synth.map_points(n, seed=n)
     q = nav.synth.map_queries(pts, NQ, seed=n + 1)
+    if os.environ.get("PRESORT"):  # host-side Morton order, to time the traversal on coherent queries
+        lo, hi = pts.min(0), pts.max(0)
+        g = np.clip(((q - lo) / (hi - lo) * 1023).astype(np.int64), 0, 1023)
+        def spread(v):
+            v = (v | (v << 16)) & 0x030000FF
+            v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3
+            v = (v | (v << 2)) & 0x09249249
+            return v
+        key = spread(g[:, 0]) | (spread(g[:, 1]) << 1) | (spread(g[:, 2]) << 2)
+        q = np.ascontiguousarray(q[np.argsort(key, kind="stable")])
     d_pts, d_q = torch.from_numpy(pts).cuda(), torch.from_numpy(q).cuda()
     i1 = torch.empty(NQ, dtype=torch.int32, device="cuda")
     d1 = torch.empty(NQ, dtype=torch.float64, device="cuda")
