@@ -254,10 +254,6 @@ def run_gpu_arm(args):
     d_frames = torch.from_numpy(frames).cuda()
     # pinned host copies for the e2e leg, pinned outputs
     h_frames = torch.from_numpy(frames).pin_memory()
-    h_feat = torch.empty((ROWS, COLS), dtype=torch.int32).pin_memory()
-    h_idx = torch.empty((ROWS, COLS), dtype=torch.int32).pin_memory()
-    h_dist = torch.empty((ROWS, COLS), dtype=torch.float64).pin_memory()
-    h_glob = torch.empty((ROWS, COLS, 3), dtype=torch.float64).pin_memory()
     binding = importlib.import_module("nav-slam_b200.binding")
     pa = binding._pos_array
 
@@ -267,12 +263,12 @@ def run_gpu_arm(args):
     # ctypes pose structs are built once: the timed loops only make the C-ABI call
     pose_c = {f: tuple(pa(p) for p in poses_for(f)) for f in range(0, K + 2 * W + 4)}
     d_base, h_base = d_frames.data_ptr(), h_frames.data_ptr()
-    outs = [(h_feat.data_ptr(), h_idx.data_ptr(), h_dist.data_ptr(), h_glob.data_ptr())]
-    h_out2 = (torch.empty((ROWS, COLS), dtype=torch.int32).pin_memory(),
-              torch.empty((ROWS, COLS), dtype=torch.int32).pin_memory(),
-              torch.empty((ROWS, COLS), dtype=torch.float64).pin_memory(),
-              torch.empty((ROWS, COLS, 3), dtype=torch.float64).pin_memory())
-    outs.append(tuple(t.data_ptr() for t in h_out2))
+    # two packed pinned result blocks [labels | nn_idx | nn_dist | global] (40 B per pixel each)
+    h_pack = torch.empty((2, NPX * 40), dtype=torch.uint8).pin_memory()
+    outs = []
+    for b in range(2):
+        p0 = h_pack[b].data_ptr()
+        outs.append((p0, p0 + NPX * 4, p0 + NPX * 8, p0 + NPX * 16))
 
     def dev_step(f):
         pp, pl, pf = pose_c[f]
@@ -335,10 +331,46 @@ def run_gpu_arm(args):
             ms, wall = float(t[0]), float(t[1]) / 1e3
         return ms, wall, launches
 
+    # the device-resident sequence is replayed through ONE C-ABI call per timed region
+    # (nav_frontend_sequence_dev: the same per-frame launches, issued from a C loop)
+    NavPos = binding.NavPos
+    def pose_block(first, count):
+        arrs = [(NavPos * count)() for _ in range(3)]
+        for i in range(count):
+            for a, p in zip(arrs, poses_for(first + i)):
+                a[i] = NavPos(*[float(v) for v in p])
+        return arrs
+
+    def timed_sequence(first_frame):
+        spin_up()
+        ctx.slam_init_dev(frame_ptr(d_frames, first_frame - 1), poses_for(first_frame - 1)[2])
+        wp = pose_block(first_frame, W)
+        kp = pose_block(first_frame + W, K)
+        if L.nav_frontend_sequence_dev(ctx.h, frame_ptr(d_frames, first_frame), W, *wp):
+            raise RuntimeError(L.nav_last_error().decode())
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        e0.record(stream)
+        if L.nav_frontend_sequence_dev(ctx.h, frame_ptr(d_frames, first_frame + W), K, *kp):
+            raise RuntimeError(L.nav_last_error().decode())
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms, ctx.launch_count() - l0
+
     clocks = ClockSampler(local)
     clocks.start()
     # --- value: device resident
-    dev_ms, _, launches = timed(dev_step, 1)
+    contiguous = (1 + W + K) <= n_frames   # the replay call needs the K frames back to back in memory
+    if contiguous:
+        dev_ms, launches = timed_sequence(1)
+    else:
+        dev_ms, _, launches = timed(dev_step, 1)
     # --- per-kernel durations over the same steps, CUDA events on the launching stream
     ctx.profile_enable(True)
     for name in ("labels", "match", "map"):
@@ -359,7 +391,7 @@ def run_gpu_arm(args):
     # --- dominant kernel roofline (SURVEY 8d algorithmic bytes)
     # counts of the last processed frame (labelled queries / map points) for the byte model
     torch.cuda.synchronize()
-    h_feat_np = h_feat.numpy()
+    h_feat_np = h_pack[0][: NPX * 4].view(torch.int32).numpy()
     nq = int((h_feat_np == 1).sum())
     n_map = nq  # consecutive frames label ~the same number of points
     n_leaf, n_sup = COLS // 16, COLS // 256

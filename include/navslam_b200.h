@@ -136,7 +136,8 @@ int nav_frontend_frame(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos_
  * this frame, the kernels of the previous one and the downloads of the one before overlap on three
  * CUDA streams.  All host pointers must be pinned (nav_host_alloc / cudaHostRegister).  The outputs
  * of a frame are complete after nav_frontend_wait(), or once two further frames have been queued
- * (use distinct output buffers for consecutive frames). */
+ * (use distinct output buffers for consecutive frames).  If the four output buffers are adjacent in
+ * host memory in the order feature | nn_idx | nn_dist | global they are filled by a single copy. */
 int nav_frontend_frame_async(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos_predict,
                              const nav_pos *pos_last, const nav_pos *pos_final, int *feature_out,
                              int32_t *nn_idx_out, double *nn_dist_out, nav_point *global_out);

@@ -261,8 +261,7 @@ extern "C" void nav_destroy(nav_ctx *c) {
         if (p) cudaFree(p);
     if (c->h_small) cudaFreeHost(c->h_small);
     for (auto &sl : c->slots) {
-        for (void *p : {(void *)sl.d_cloud, (void *)sl.d_nn_dist, (void *)sl.d_global, (void *)sl.d_labels,
-                        (void *)sl.d_nn_idx})
+        for (void *p : {(void *)sl.d_cloud, (void *)sl.d_labels})  // the other outputs live inside d_labels
             if (p) cudaFree(p);
         for (cudaEvent_t e : {sl.in_done, sl.compute_done, sl.out_done})
             if (e) cudaEventDestroy(e);
@@ -771,10 +770,12 @@ static int async_setup(nav_ctx *c) {
     CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
     for (auto &sl : c->slots) {
         CU(cudaMalloc((void **)&sl.d_cloud, c->ntot * 24));
-        CU(cudaMalloc((void **)&sl.d_global, c->ntot * 24));
-        CU(cudaMalloc((void **)&sl.d_nn_dist, c->ntot * 8));
-        CU(cudaMalloc((void **)&sl.d_labels, c->ntot * 4));
-        CU(cudaMalloc((void **)&sl.d_nn_idx, c->ntot * 4));
+        // the four outputs of a slot are one allocation [labels | nn_idx | nn_dist | global], so that a
+        // caller whose host buffers are laid out the same way gets them with a single copy
+        CU(cudaMalloc((void **)&sl.d_labels, c->ntot * 40));
+        sl.d_nn_idx = sl.d_labels + c->ntot;
+        sl.d_nn_dist = (double *)(sl.d_nn_idx + c->ntot);
+        sl.d_global = sl.d_nn_dist + c->ntot;
         CU(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
@@ -823,10 +824,17 @@ extern "C" int nav_frontend_frame_async(nav_ctx *c, const nav_point *cloud, cons
     c->cloud_resident = false;
     // copy-out
     CU(cudaStreamWaitEvent(c->s_out, sl.compute_done, 0));
-    if (feature_out) CU(cudaMemcpyAsync(feature_out, sl.d_labels, c->ntot * 4, cudaMemcpyDeviceToHost, c->s_out));
-    if (nn_idx_out) CU(cudaMemcpyAsync(nn_idx_out, sl.d_nn_idx, c->ntot * 4, cudaMemcpyDeviceToHost, c->s_out));
-    if (nn_dist_out) CU(cudaMemcpyAsync(nn_dist_out, sl.d_nn_dist, c->ntot * 8, cudaMemcpyDeviceToHost, c->s_out));
-    if (global_out) CU(cudaMemcpyAsync(global_out, sl.d_global, c->ntot * 24, cudaMemcpyDeviceToHost, c->s_out));
+    const bool packed = feature_out && nn_idx_out == feature_out + c->ntot &&
+                        (void *)nn_dist_out == (void *)(nn_idx_out + c->ntot) &&
+                        (void *)global_out == (void *)(nn_dist_out + c->ntot);
+    if (packed) {
+        CU(cudaMemcpyAsync(feature_out, sl.d_labels, c->ntot * 40, cudaMemcpyDeviceToHost, c->s_out));
+    } else {
+        if (feature_out) CU(cudaMemcpyAsync(feature_out, sl.d_labels, c->ntot * 4, cudaMemcpyDeviceToHost, c->s_out));
+        if (nn_idx_out) CU(cudaMemcpyAsync(nn_idx_out, sl.d_nn_idx, c->ntot * 4, cudaMemcpyDeviceToHost, c->s_out));
+        if (nn_dist_out) CU(cudaMemcpyAsync(nn_dist_out, sl.d_nn_dist, c->ntot * 8, cudaMemcpyDeviceToHost, c->s_out));
+        if (global_out) CU(cudaMemcpyAsync(global_out, sl.d_global, c->ntot * 24, cudaMemcpyDeviceToHost, c->s_out));
+    }
     CU(cudaEventRecord(sl.out_done, c->s_out));
     c->async_frames++;
     return 0;

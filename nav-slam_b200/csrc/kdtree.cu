@@ -367,6 +367,74 @@ k_kd_nn(const KdNode *__restrict__ nodes, int n, const double *__restrict__ quer
     dist_out[qi] = bidx >= 0 ? __dsqrt_rn(best) : INFINITY;
 }
 
+// The same search with a short explicit stack (thread-local memory, L1 resident): far children are
+// pushed with their plane distance on the way down and popped (or discarded) later, so no ancestor
+// is ever re-read and nothing climbs level by level.  Visits exactly the nodes the stackless kernel
+// visits (same pruning rule, same lexicographic compare) -> identical answers.
+__global__ void __launch_bounds__(128)
+k_kd_nn_stack(const KdNode *__restrict__ nodes, int n, const double *__restrict__ queries, long long nq,
+              const int *__restrict__ perm, int *__restrict__ idx_out, double *__restrict__ dist_out) {
+    const long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (slot >= nq) return;
+    const long long qi = perm ? perm[slot] : slot;
+    if (n <= 0) {
+        idx_out[qi] = -1;
+        dist_out[qi] = INFINITY;
+        return;
+    }
+    const double qx = queries[qi * 3], qy = queries[qi * 3 + 1], qz = queries[qi * 3 + 2];
+    double best = INFINITY;
+    int bidx = -1;
+    int st_lo[32], st_hi[32], st_d[32];
+    double st_plane[32];
+    int sp = 0;
+    int lo = 0, hi = n, depth = 0;
+    while (true) {
+        while (lo < hi) {
+            const int mid = lo + ((hi - lo) >> 1);
+            double x, y, z;
+            int idx;
+            load_node(nodes, mid, x, y, z, idx);
+            const double d = dsq3(dsub(x, qx), dsub(y, qy), dsub(z, qz));
+            if (d < best || (d == best && idx < bidx)) {
+                best = d;
+                bidx = idx;
+            }
+            const int axis = depth % 3;
+            const double diff = dsub(axis == 0 ? qx : (axis == 1 ? qy : qz), axis == 0 ? x : (axis == 1 ? y : z));
+            const bool near_right = !(diff < 0.0);
+            const int flo = near_right ? lo : mid + 1, fhi = near_right ? mid : hi;
+            if (flo < fhi) {
+                st_lo[sp] = flo;
+                st_hi[sp] = fhi;
+                st_d[sp] = depth + 1;
+                st_plane[sp] = dmul(diff, diff);
+                ++sp;
+            }
+            if (near_right)
+                lo = mid + 1;
+            else
+                hi = mid;
+            ++depth;
+        }
+        // next pending far subtree whose plane is still within reach (NaN planes are never pruned)
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (!(st_plane[sp] > best)) {
+                lo = st_lo[sp];
+                hi = st_hi[sp];
+                depth = st_d[sp];
+                found = true;
+                break;
+            }
+        }
+        if (!found) break;
+    }
+    idx_out[qi] = bidx;
+    dist_out[qi] = bidx >= 0 ? __dsqrt_rn(best) : INFINITY;
+}
+
 cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const double *d_queries, size_t nq,
                   int *d_idx, double *d_dist, int sm_count, cudaStream_t stream, uint64_t *launches) {
     if (nq == 0) return cudaSuccess;
@@ -377,8 +445,13 @@ cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const d
     // cost ~75 us, so it is off unless NAV_KD_SORT=1 (e.g. for much larger query sets).
     static const int sort_mode = getenv("NAV_KD_SORT") ? atoi(getenv("NAV_KD_SORT")) : 0;
     const bool sort_queries = sort_mode && d_bbox && n >= 4096 && nq >= 8192 && nq < (size_t)0x7fffffff;
+    static const int use_stack = getenv("NAV_KD_STACK") ? atoi(getenv("NAV_KD_STACK")) : 0;
     if (!sort_queries) {
-        k_kd_nn<<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx, d_dist);
+        if (use_stack)
+            k_kd_nn_stack<<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx,
+                                                        d_dist);
+        else
+            k_kd_nn<<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx, d_dist);
         if (launches) *launches += 1;
         return cudaGetLastError();
     }

@@ -35,6 +35,9 @@
 namespace nav {
 
 constexpr unsigned kFull = 0xffffffffu;
+#ifndef NAV_MATCH_MIN_CTAS
+#define NAV_MATCH_MIN_CTAS 4  // 64 registers/thread: keeps the fp32 query bracket live instead of re-converting it
+#endif
 static_assert(kTile == kChunk * kChunksPerSuper, "one CTA tile = one super block of 16 leaf blocks");
 
 __device__ __forceinline__ P3 load_p3(const double *__restrict__ p) {
@@ -216,7 +219,7 @@ struct MapSmem {
 // grid as k_frame_map.  kFusedLabels: compute the labels of the tile here (and store them);
 // otherwise read them from `labels`.
 template <bool kFusedLabels>
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kTile, NAV_MATCH_MIN_CTAS)
 k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap map, MatchOut out,
               const __grid_constant__ PoseBatch poses, int rows, int cols, int tiles_per_row,
               unsigned *__restrict__ n_exact) {
