@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "nav_kdtree.cuh"
@@ -164,7 +165,8 @@ struct nav_ctx {
     double *d_stats = nullptr;      // [n_seq][5] sufficient statistics of the translation fit
     unsigned *d_n_exact = nullptr;  // labels the fp32 filter could not decide (exact re-evaluations)
     int *d_labels = nullptr, *d_nn_idx = nullptr;
-    RowMap map = {};
+    RowMap map = {};      // the map the next match searches (frame mapped last)
+    RowMap map_alt = {};  // second buffer: the fused frame kernel builds the next map here, then they swap
     nav_corr *d_corr_rows = nullptr, *d_corr = nullptr;
     int *d_corr_row_count = nullptr, *d_corr_total = nullptr;
     int *d_dist = nullptr;
@@ -254,7 +256,8 @@ extern "C" void nav_destroy(nav_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->d_cloud, c->d_global, c->d_curv, c->d_nn_dist, c->d_labels, c->d_nn_idx, c->map.pts,
-                    c->map.mask, c->d_n_exact, c->d_stats, c->map.box, c->map.sbox, c->d_corr_rows, c->d_corr,
+                    c->map.mask, c->d_n_exact, c->d_stats, c->map.box, c->map.sbox, c->map_alt.pts, c->map_alt.mask,
+                    c->map_alt.box, c->map_alt.sbox, c->d_corr_rows, c->d_corr,
                     c->d_corr_row_count, c->d_corr_total, c->d_dist, c->d_tan_col, c->d_tan_row, c->d_flat,
                     c->d_flat_count};
     for (void *p : ptrs)
@@ -334,6 +337,12 @@ extern "C" nav_ctx *nav_create(int rows, int cols, int device, int n_seq) {
     ALLOC(c->d_stats, (size_t)n_seq * 5 * 8);
     ALLOC(c->map.box, nr * c->map.n_chunks * 32);
     ALLOC(c->map.sbox, nr * c->map.n_super * 32);
+    c->map_alt.n_chunks = c->map.n_chunks;
+    c->map_alt.n_super = c->map.n_super;
+    ALLOC(c->map_alt.pts, nt * 24);
+    ALLOC(c->map_alt.mask, nr * c->map.n_chunks * 4);
+    ALLOC(c->map_alt.box, nr * c->map.n_chunks * 32);
+    ALLOC(c->map_alt.sbox, nr * c->map.n_super * 32);
     ALLOC(c->d_corr_rows, nt * sizeof(nav_corr));
     ALLOC(c->d_corr, nt * sizeof(nav_corr));
     ALLOC(c->d_corr_row_count, nr * 4);
@@ -469,6 +478,23 @@ static void run_match(nav_ctx *c, const double *d_cloud, const PoseBatch &poses,
                            c->cols, c->stream);
         c->launches += 2;
     }
+}
+
+static PoseBatch pose_batch(const nav_ctx *c, const nav_pos *pos, const nav_pos *last);
+
+// the whole front-end frame in ONE launch: labels (a3) + queries (a7) + exact per-row NN against the
+// current map (a6) + the next map from the final pose (a7, a4/a5) into the other map buffer
+static void run_frame_fused(nav_ctx *c, const double *d_cloud, int *d_labels, int *d_nn_idx, double *d_nn_dist,
+                            const nav_pos *pos_predict, const nav_pos *pos_last, const nav_pos *pos_final) {
+    MatchOut out = {d_nn_idx, d_nn_dist, c->d_corr_rows, c->d_corr_row_count};
+    const PoseBatch loc = pose_batch(c, pos_predict, pos_last), fin = pose_batch(c, pos_final, nullptr);
+    {
+        ProfScope ps(c, &c->prof_match);
+        launch_frame_match(d_cloud, d_labels, true, c->map, out, loc, c->n_seq, c->rows, c->cols, c->d_n_exact,
+                           c->stream, &c->map_alt, &fin);
+    }
+    c->launches++;
+    std::swap(c->map, c->map_alt);
 }
 
 static PoseBatch pose_batch(const nav_ctx *c, const nav_pos *pos, const nav_pos *last) {
@@ -749,8 +775,7 @@ extern "C" int nav_frontend_frame(nav_ctx *c, const nav_point *cloud, const nav_
     if (!c->have_map) return fail("nav_frontend_frame: call nav_slam_init first");
     if (c->stage.reserve(c->ntot * (24 + 24 + 4 + 4 + 8) + 4096, c->stream)) return fail("nav_frontend_frame: staging");
     if (upload_cloud(c, cloud, "nav_frontend_frame")) return 1;
-    run_match(c, c->d_cloud, pose_batch(c, pos_predict, pos_last), false);
-    run_map(c, c->d_cloud, pose_batch(c, pos_final, nullptr));
+    run_frame_fused(c, c->d_cloud, c->d_labels, c->d_nn_idx, c->d_nn_dist, pos_predict, pos_last, pos_final);
     c->cloud_resident = true;
     if (feature_out && c->stage.d2h(feature_out, c->d_labels, c->ntot * 4, c->stream)) return fail("nav_frontend_frame: D2H");
     if (nn_idx_out && c->stage.d2h(nn_idx_out, c->d_nn_idx, c->ntot * 4, c->stream)) return fail("nav_frontend_frame: D2H");
@@ -803,23 +828,10 @@ extern "C" int nav_frontend_frame_async(nav_ctx *c, const nav_point *cloud, cons
     // kernels: need the upload, and the slot's output buffers released by the downloads of frame t-2
     CU(cudaStreamWaitEvent(c->stream, sl.in_done, 0));
     if (reused) CU(cudaStreamWaitEvent(c->stream, sl.out_done, 0));
-    {
-        MatchOut out = {sl.d_nn_idx, sl.d_nn_dist, c->d_corr_rows, c->d_corr_row_count};
-        {
-            ProfScope ps(c, &c->prof_match);
-            launch_frame_match(sl.d_cloud, sl.d_labels, true, c->map, out, pose_batch(c, pos_predict, pos_last),
-                               c->n_seq, c->rows, c->cols, c->d_n_exact, c->stream);
-        }
-        {
-            ProfScope ps(c, &c->prof_map);
-            launch_frame_map(sl.d_cloud, sl.d_labels, c->map, pose_batch(c, pos_final, nullptr), c->n_seq, c->rows,
-                             c->cols, c->stream);
-        }
-        c->launches += 2;
-        // the mapped cloud is persistent state (next frame's map): hand the copy-out stream a snapshot
-        if (global_out)
-            CU(cudaMemcpyAsync(sl.d_global, c->map.pts, c->ntot * 24, cudaMemcpyDeviceToDevice, c->stream));
-    }
+    run_frame_fused(c, sl.d_cloud, sl.d_labels, sl.d_nn_idx, sl.d_nn_dist, pos_predict, pos_last, pos_final);
+    // the mapped cloud is persistent state (the next frame searches it): hand the copy-out stream a
+    // snapshot that sits next to the other outputs of the slot
+    if (global_out) CU(cudaMemcpyAsync(sl.d_global, c->map.pts, c->ntot * 24, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaEventRecord(sl.compute_done, c->stream));
     c->cloud_resident = false;
     // copy-out
@@ -868,9 +880,8 @@ extern "C" int nav_frontend_frame_dev(nav_ctx *c, const void *dev_cloud, const n
     CTX_ENTER(c, "nav_frontend_frame_dev");
     if (!dev_cloud || !pos_predict || !pos_last || !pos_final) return fail("nav_frontend_frame_dev: null argument");
     if (!c->have_map) return fail("nav_frontend_frame_dev: call nav_slam_init_dev first");
-    const double *cl = (const double *)dev_cloud;
-    run_match(c, cl, pose_batch(c, pos_predict, pos_last), false);
-    run_map(c, cl, pose_batch(c, pos_final, nullptr));
+    run_frame_fused(c, (const double *)dev_cloud, c->d_labels, c->d_nn_idx, c->d_nn_dist, pos_predict, pos_last,
+                    pos_final);
     c->cloud_resident = false;
     CU(cudaGetLastError());
     return 0;
@@ -886,8 +897,7 @@ extern "C" int nav_frontend_sequence_dev(nav_ctx *c, const void *dev_frames, siz
     for (size_t f = 0; f < n_frames; ++f) {
         const double *cl = base + f * c->ntot * 3;
         const size_t o = f * (size_t)c->n_seq;
-        run_match(c, cl, pose_batch(c, pos_predict + o, pos_last + o), false);
-        run_map(c, cl, pose_batch(c, pos_final + o, nullptr));
+        run_frame_fused(c, cl, c->d_labels, c->d_nn_idx, c->d_nn_dist, pos_predict + o, pos_last + o, pos_final + o);
     }
     c->cloud_resident = false;
     CU(cudaGetLastError());

@@ -36,9 +36,12 @@ int configure_row_kernels(int cols);  // opt in to large dynamic shared memory; 
 
 void launch_frame_map(const double *cloud, const int *labels, const RowMap &map, const PoseBatch &poses,
                       int n_seq, int rows, int cols, cudaStream_t stream);
+// map_next/final_poses non-null: the kernel also builds the next map (frame transformed with its final
+// pose) into *map_next, which must be a different buffer than `map`
 void launch_frame_match(const double *cloud, int *labels, bool fused_labels, const RowMap &map,
                         const MatchOut &out, const PoseBatch &poses, int n_seq, int rows, int cols,
-                        unsigned *n_exact, cudaStream_t stream);
+                        unsigned *n_exact, cudaStream_t stream, const RowMap *map_next = nullptr,
+                        const PoseBatch *final_poses = nullptr);
 void launch_dedupe(const double *cloud, const int *labels, const RowMap &map, const MatchOut &out,
                    const PoseBatch &poses, int n_seq, int rows, int cols, cudaStream_t stream);
 void launch_gather_corr(const nav_corr *corr_rows, const int *corr_row_count, nav_corr *corr_out,

@@ -64,25 +64,15 @@ __device__ __forceinline__ void half_minmax(double &lo, double &hi) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// grid = n_rows * tiles_per_row CTAs of kTile threads; thread = one column
-__global__ void __launch_bounds__(kTile)
-k_frame_map(const double *__restrict__ cloud, const int *__restrict__ labels, RowMap map,
-            const __grid_constant__ PoseBatch poses, int rows, int cols, int tiles_per_row) {
-    __shared__ float4 s_lo[kChunksPerSuper], s_hi[kChunksPerSuper];
-    const int rid = blockIdx.x / tiles_per_row;  // sequence * rows + row
-    const int tile = blockIdx.x % tiles_per_row;
-    const int seq = rid / rows;
-    const long long base = (long long)rid * cols;
-    const PoseXf &pose = poses.p[seq];
-    const int c = tile * kTile + threadIdx.x;
-    const bool valid = c < cols;
+// One (row, 256-column tile) of the map: transform the thread's own column, write the global
+// cloud, the 16-bit label masks, the leaf boxes and the tile's super box.  Called by all kTile
+// threads of the CTA (contains one __syncthreads).
+__device__ __forceinline__ void map_tile(bool lab, bool valid, const P3 &p, const PoseXf &pose, const RowMap &map,
+                                         int rid, int tile, int c, long long base, float4 *s_lo, float4 *s_hi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, l16 = lane & 15;
-
-    bool lab = false;
     P3 g = {0, 0, 0};
     if (valid) {
-        lab = labels[base + c] == 1;
-        g = xf_point(pose, ldg_p3(cloud + (base + c) * 3));
+        g = xf_point(pose, p);
         store_p3(map.pts + (base + c) * 3, g);
     }
     const unsigned ballot = __ballot_sync(kFull, lab);
@@ -129,6 +119,25 @@ k_frame_map(const double *__restrict__ cloud, const int *__restrict__ labels, Ro
             o[1] = b;
         }
     }
+}
+
+// grid = n_rows * tiles_per_row CTAs of kTile threads; thread = one column
+__global__ void __launch_bounds__(kTile)
+k_frame_map(const double *__restrict__ cloud, const int *__restrict__ labels, RowMap map,
+            const __grid_constant__ PoseBatch poses, int rows, int cols, int tiles_per_row) {
+    __shared__ float4 s_lo[kChunksPerSuper], s_hi[kChunksPerSuper];
+    const int rid = blockIdx.x / tiles_per_row;  // sequence * rows + row
+    const int tile = blockIdx.x % tiles_per_row;
+    const long long base = (long long)rid * cols;
+    const int c = tile * kTile + threadIdx.x;
+    const bool valid = c < cols;
+    bool lab = false;
+    P3 p = {0, 0, 0};
+    if (valid) {
+        lab = labels[base + c] == 1;
+        p = ldg_p3(cloud + (base + c) * 3);
+    }
+    map_tile(lab, valid, p, poses.p[rid / rows], map, rid, tile, c, base, s_lo, s_hi);
 }
 
 // exclusive prefix of `pred` over the block (thread order), plus the block total
@@ -217,12 +226,14 @@ struct MapSmem {
 };
 
 // grid as k_frame_map.  kFusedLabels: compute the labels of the tile here (and store them);
-// otherwise read them from `labels`.
-template <bool kFusedLabels>
+// otherwise read them from `labels`.  kFuseMap: also build the NEXT map (this frame transformed with
+// its final pose) into map_next -- a second buffer, because neighbouring CTAs are still searching the
+// current one -- which makes the whole front-end frame a single launch.
+template <bool kFusedLabels, bool kFuseMap>
 __global__ void __launch_bounds__(kTile, NAV_MATCH_MIN_CTAS)
 k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap map, MatchOut out,
               const __grid_constant__ PoseBatch poses, int rows, int cols, int tiles_per_row,
-              unsigned *__restrict__ n_exact) {
+              unsigned *__restrict__ n_exact, RowMap map_next, const __grid_constant__ PoseBatch final_poses) {
     __shared__ StencilSmem s;
     const int rid = blockIdx.x / tiles_per_row;
     const int tile = blockIdx.x % tiles_per_row;
@@ -268,6 +279,21 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
     if (c < cols && label != 1) {
         out.nn_idx[base + c] = -1;
         out.nn_dist[base + c] = -1.0;
+    }
+    if (kFuseMap) {  // a7 + a4/a5 for the next frame's search, into the other map buffer
+        __shared__ float4 s_lo[kChunksPerSuper], s_hi[kChunksPerSuper];
+        P3 own = {0, 0, 0};
+        if (c < cols) {
+            if (kFusedLabels) {
+                const double *sp = s.pts + (threadIdx.x + kHalo) * 3;
+                own.x = sp[0];
+                own.y = sp[1];
+                own.z = sp[2];
+            } else {
+                own = ldg_p3(cloud + (base + c) * 3);
+            }
+        }
+        map_tile(label == 1, c < cols, own, final_poses.p[seq], map_next, rid, tile, c, base, s_lo, s_hi);
     }
     // compact the labelled columns of the tile so that the search runs on densely populated warps
     cp_async_wait_all();
@@ -329,16 +355,27 @@ void launch_frame_map(const double *cloud, const int *labels, const RowMap &map,
 
 void launch_frame_match(const double *cloud, int *labels, bool fused_labels, const RowMap &map,
                         const MatchOut &out, const PoseBatch &poses, int n_seq, int rows, int cols,
-                        unsigned *n_exact, cudaStream_t stream) {
+                        unsigned *n_exact, cudaStream_t stream, const RowMap *map_next,
+                        const PoseBatch *final_poses) {
     const int tiles = div_up(cols, kTile);
     const int grid = n_seq * rows * tiles;
-    if (fused_labels)
-        k_frame_match<true><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles, n_exact);
-    else
-        k_frame_match<false><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles, n_exact);
+    if (map_next && final_poses) {
+        if (fused_labels)
+            k_frame_match<true, true><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles,
+                                                                  n_exact, *map_next, *final_poses);
+        else
+            k_frame_match<false, true><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles,
+                                                                   n_exact, *map_next, *final_poses);
+    } else {
+        if (fused_labels)
+            k_frame_match<true, false><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles,
+                                                                   n_exact, map, poses);
+        else
+            k_frame_match<false, false><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles,
+                                                                    n_exact, map, poses);
+    }
 }
 
-// ---------------------------------------------------------------------------------------------
 constexpr int kRowThreads = 512;
 
 // per-row dedupe, src/slam.c:247-283: one entry per matched map point; the query with the smallest
