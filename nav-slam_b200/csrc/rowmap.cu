@@ -324,13 +324,36 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
     const int seed = qc / kChunk;
     scan_leaf(sm.pts + (seed - leaf0) * kChunk * 3, sm.mask[seed - leaf0], seed * kChunk, q, best, bcol);
     best_up = __double2float_ru(best);
+    // The leaves next to the seed come first, addressed RELATIVE to the seed: the lanes of a warp hold
+    // queries of neighbouring columns with different seeds, and stepping through "seed-1, seed+1, ..."
+    // together lets every lane scan its own neighbour in the same loop iteration.  (Walking absolute
+    // leaf indices instead made the warp execute the union of all lanes' neighbour scans.)
+    constexpr int kNear = 2;
+#pragma unroll
+    for (int d = 1; d <= kNear; ++d) {
+#pragma unroll
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+            const int lf = seed + sgn * d, j = lf - leaf0;
+            if (lf < 0 || lf >= n_leaf) continue;
+            const bool near_leaf = j >= 0 && j < kNbLeaves;
+            const float4 blo = near_leaf ? sm.box[j * 2] : __ldg(m_box + lf * 2);
+            const float4 bhi = near_leaf ? sm.box[j * 2 + 1] : __ldg(m_box + lf * 2 + 1);
+            if (box_lower_bound32(blo, bhi, q32) > best_up) continue;
+            if (near_leaf)
+                scan_leaf(sm.pts + j * kChunk * 3, sm.mask[j], lf * kChunk, q, best, bcol);
+            else
+                scan_leaf(m_pts + (long long)lf * kChunk * 3, __ldg(m_mask + lf), lf * kChunk, q, best, bcol);
+            best_up = __double2float_ru(best);
+        }
+    }
+    // everything else through the box hierarchy (exactness does not depend on the order of visits)
     for (int sc = 0; sc < n_sup; ++sc) {
         const float4 slo = sup_in_smem ? sm.sbox[sc * 2] : __ldg(m_sbox + sc * 2);
         const float4 shi = sup_in_smem ? sm.sbox[sc * 2 + 1] : __ldg(m_sbox + sc * 2 + 1);
         if (box_lower_bound32(slo, shi, q32) > best_up) continue;
         const int l1 = min(n_leaf, (sc + 1) * kChunksPerSuper);
         for (int lf = sc * kChunksPerSuper; lf < l1; ++lf) {
-            if (lf == seed) continue;
+            if (lf >= seed - kNear && lf <= seed + kNear) continue;  // already visited
             const int j = lf - leaf0;
             const bool near_leaf = j >= 0 && j < kNbLeaves;
             const float4 blo = near_leaf ? sm.box[j * 2] : __ldg(m_box + lf * 2);
