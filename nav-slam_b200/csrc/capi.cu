@@ -999,7 +999,7 @@ static nav_kdtree *kd_new(int device, size_t n) {
     t->n = n;
     cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc((void **)&t->d_bbox, 48) != cudaSuccess ||
+        cudaMalloc((void **)&t->d_bbox, 64) != cudaSuccess ||  // 48 B box + 8 B work-queue counter
         (n && (cudaMalloc((void **)&t->d_nodes, n * sizeof(KdNode)) != cudaSuccess ||
                cudaMalloc((void **)&t->d_pts, n * 24) != cudaSuccess))) {
         fail("nav_kdtree_build: device allocation for %zu points failed", n);
@@ -1074,7 +1074,7 @@ extern "C" int nav_kdtree_nn_batch_dev(nav_kdtree *t, const void *dev_queries, s
     CU(cudaSetDevice(t->device));
     cudaStream_t s = (cudaStream_t)cuda_stream;  // 0 = legacy default stream
     CU(kd_nn(t->d_nodes, t->n, t->d_bbox, (const double *)dev_queries, nq, (int *)dev_idx, (double *)dev_dist,
-             t->sm_count, s, &t->launches));
+             t->sm_count, s, &t->launches, (unsigned long long *)(t->d_bbox + 6)));
     return 0;
 }
 
@@ -1096,7 +1096,8 @@ extern "C" int nav_kdtree_nn_batch(nav_kdtree *t, const nav_point *queries, size
         t->q_cap = nq;
     }
     CU(cudaMemcpyAsync(t->d_q, queries, nq * 24, cudaMemcpyHostToDevice, t->stream));
-    CU(kd_nn(t->d_nodes, t->n, t->d_bbox, t->d_q, nq, t->d_idx, t->d_dist, t->sm_count, t->stream, &t->launches));
+    CU(kd_nn(t->d_nodes, t->n, t->d_bbox, t->d_q, nq, t->d_idx, t->d_dist, t->sm_count, t->stream, &t->launches,
+             (unsigned long long *)(t->d_bbox + 6)));
     CU(cudaMemcpyAsync(idx_out, t->d_idx, nq * 4, cudaMemcpyDeviceToHost, t->stream));
     CU(cudaMemcpyAsync(dist_out, t->d_dist, nq * 8, cudaMemcpyDeviceToHost, t->stream));
     if (nearest_out && t->n) {

@@ -27,6 +27,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "nav_kdtree.cuh"
 
@@ -367,6 +368,115 @@ k_kd_nn(const KdNode *__restrict__ nodes, int n, const double *__restrict__ quer
     dist_out[qi] = bidx >= 0 ? __dsqrt_rn(best) : INFINITY;
 }
 
+// Converged variant of the stackless search (the default).  Every lane performs exactly one "node
+// step" per loop iteration -- first visit (distance + descend) or return visit (far-side test) share
+// one instruction stream -- so the warp does not alternate between a descent path and a climb path;
+// lanes that finish pull the next query from a global counter instead of idling until the slowest
+// lane of the warp is done; and the climb skips, with integer arithmetic only, every ancestor whose
+// far side is already known to be out of reach (a per-level "pending" bit, cleared at the first
+// visit when plane^2 > best).  Same nodes compared, same lexicographic rule: identical answers.
+__global__ void __launch_bounds__(128)
+k_kd_nn_conv(const KdNode *__restrict__ nodes, int n, const double *__restrict__ queries, long long nq,
+             int *__restrict__ idx_out, double *__restrict__ dist_out, unsigned long long *__restrict__ counter) {
+    const unsigned lane = threadIdx.x & 31u;
+    long long qi = -1;
+    bool done = false, fresh = true;
+    double qx = 0, qy = 0, qz = 0, best = INFINITY;
+    int bidx = -1, lo = 0, hi = 0, depth = 0;
+    unsigned path = 0, par = 0, pend = 0;
+    while (true) {
+        // ---- refill: lanes without a query take the next ones (one atomic per warp)
+        const unsigned need = __ballot_sync(0xffffffffu, qi < 0 && !done);
+        if (need) {
+            unsigned long long base = 0;
+            const int leader = __ffs(need) - 1;
+            if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (qi < 0 && !done) {
+                const long long mine = (long long)base + __popc(need & ((1u << lane) - 1u));
+                if (mine < nq) {
+                    qi = mine;
+                    qx = queries[qi * 3];
+                    qy = queries[qi * 3 + 1];
+                    qz = queries[qi * 3 + 2];
+                    best = INFINITY;
+                    bidx = -1;
+                    lo = 0;
+                    hi = n;
+                    depth = 0;
+                    path = par = pend = 0;
+                    fresh = true;
+                } else {
+                    done = true;
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, done)) break;
+        if (done) continue;
+        // ---- one node step
+        const int mid = lo + ((hi - lo) >> 1);
+        const int axis = depth - 3 * ((depth * 11) >> 5);  // depth % 3 for depth < 32
+        const unsigned bit = 1u << depth;
+        double x, y, z;
+        int idx;
+        load_node(nodes, mid, x, y, z, idx);
+        const double diff = dsub(axis == 0 ? qx : (axis == 1 ? qy : qz), axis == 0 ? x : (axis == 1 ? y : z));
+        const double plane = dmul(diff, diff);
+        if (fresh) {
+            // operand order root - target (utils/kdtree.c:16); squared, so the sign is immaterial
+            const double d = dsq3(dsub(x, qx), dsub(y, qy), dsub(z, qz));
+            if (d < best || (d == best && idx < bidx)) {
+                best = d;
+                bidx = idx;
+            }
+            const bool near_right = !(diff < 0.0);  // target < node -> left, else right (kdtree.c:130-141)
+            par = (par & ~bit) | ((unsigned)((hi - lo) & 1) << depth);
+            path = (path & ~bit) | ((unsigned)near_right << depth);
+            const bool far_nonempty = near_right ? (lo < mid) : (mid + 1 < hi);
+            // '<=' on squares keeps exact ties reachable (lowest index wins); NaN planes are never pruned
+            pend = (far_nonempty && !(plane > best)) ? (pend | bit) : (pend & ~bit);
+            const int clo = near_right ? mid + 1 : lo, chi = near_right ? hi : mid;
+            if (clo < chi) {
+                lo = clo;
+                hi = chi;
+                ++depth;
+                continue;
+            }
+            fresh = false;  // empty near side: handle this node as a return visit right away
+        }
+        if ((pend & bit) && !(plane > best)) {  // far side still within reach: go there
+            const bool near_right = (path >> depth) & 1u;
+            pend &= ~bit;
+            path ^= bit;
+            if (near_right)
+                hi = mid;
+            else
+                lo = mid + 1;
+            ++depth;
+            fresh = true;
+            continue;
+        }
+        pend &= ~bit;
+        const unsigned below = pend & (bit - 1u);
+        if (!below) {  // nothing pending anywhere above: this query is finished
+            idx_out[qi] = bidx;
+            dist_out[qi] = bidx >= 0 ? __dsqrt_rn(best) : INFINITY;
+            qi = -1;
+            continue;
+        }
+        const int target = 31 - __clz(below);
+        while (depth > target) {  // integer-only climb; ranges follow from (side taken, size parity)
+            --depth;
+            const int cs = hi - lo;
+            const unsigned parity = (par >> depth) & 1u;
+            if ((path >> depth) & 1u)
+                lo = hi - (2 * cs + 1 + (parity ? 0 : 1));
+            else
+                hi = lo + (2 * cs + (int)parity);
+        }
+    }
+}
+
 // The same search with a short explicit stack (thread-local memory, L1 resident): far children are
 // pushed with their plane distance on the way down and popped (or discarded) later, so no ancestor
 // is ever re-read and nothing climbs level by level.  Visits exactly the nodes the stackless kernel
@@ -436,7 +546,8 @@ k_kd_nn_stack(const KdNode *__restrict__ nodes, int n, const double *__restrict_
 }
 
 cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const double *d_queries, size_t nq,
-                  int *d_idx, double *d_dist, int sm_count, cudaStream_t stream, uint64_t *launches) {
+                  int *d_idx, double *d_dist, int sm_count, cudaStream_t stream, uint64_t *launches,
+                  unsigned long long *d_counter) {
     if (nq == 0) return cudaSuccess;
     const int threads = 128;
     const unsigned grid = (unsigned)((nq + threads - 1) / threads);
@@ -445,7 +556,22 @@ cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const d
     // cost ~75 us, so it is off unless NAV_KD_SORT=1 (e.g. for much larger query sets).
     static const int sort_mode = getenv("NAV_KD_SORT") ? atoi(getenv("NAV_KD_SORT")) : 0;
     const bool sort_queries = sort_mode && d_bbox && n >= 4096 && nq >= 8192 && nq < (size_t)0x7fffffff;
-    static const int use_stack = getenv("NAV_KD_STACK") ? atoi(getenv("NAV_KD_STACK")) : 0;
+    // Kernel choice by measurement on B200 (131 072 queries; profiles/README.md): the plain stackless
+    // kernel wins up to ~1 M points (127 vs 137 us), the converged work-refilling kernel wins on
+    // maps that no longer fit in L2 (10 M points: 199 vs 219 us); a short explicit stack is faster only
+    // around 64 K points and slower at 10 M, so it stays opt-in.  NAV_KD_KERNEL = plain|conv|stack overrides.
+    const char *kk = getenv("NAV_KD_KERNEL");
+    const int use_stack = kk && !strcmp(kk, "stack");
+    const bool use_conv = kk ? !strcmp(kk, "conv") : n >= ((size_t)1 << 22);
+    if (!sort_queries && use_conv && d_counter && n > 0) {
+        cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
+        unsigned pgrid = (unsigned)sm_count * 12u;  // 12 x 128 threads = 48 warps per SM (40 registers)
+        if ((unsigned long long)pgrid * threads > nq) pgrid = (unsigned)((nq + threads - 1) / threads);
+        k_kd_nn_conv<<<pgrid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, d_idx, d_dist,
+                                                    d_counter);
+        if (launches) *launches += 1;
+        return cudaGetLastError();
+    }
     if (!sort_queries) {
         if (use_stack)
             k_kd_nn_stack<<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx,

@@ -14,7 +14,8 @@ static_assert(sizeof(KdNode) == 32, "one DRAM sector per node");
 cudaError_t kd_build(const double *d_pts, size_t n, KdNode *d_nodes, double *d_bbox, int sm_count,
                      cudaStream_t stream, uint64_t *launches);
 cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const double *d_queries, size_t nq,
-                  int *d_idx, double *d_dist, int sm_count, cudaStream_t stream, uint64_t *launches);
+                  int *d_idx, double *d_dist, int sm_count, cudaStream_t stream, uint64_t *launches,
+                  unsigned long long *d_counter);  // d_counter: 8 bytes of device scratch (work queue head)
 cudaError_t bf_nn(const double *d_pts, size_t n, const double *d_queries, size_t nq, int *d_idx, double *d_dist,
                   cudaStream_t stream);
 
