@@ -1130,9 +1130,24 @@ extern "C" int nav_bruteforce_nn_batch_dev(int device, const void *dev_points, s
     if (nav_device_count() == 0) return fail("nav_bruteforce_nn_batch_dev: no CUDA device");
     if (nq && (!dev_queries || !dev_idx || !dev_dist || (n && !dev_points)))
         return fail("nav_bruteforce_nn_batch_dev: null argument");
-    if (use_tensor_cores)
-        return fail("nav_bruteforce_nn_batch_dev: the tensor-core candidate path is not built in this version");
     CU(cudaSetDevice(device));
+    if (use_tensor_cores) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        static const bool want_stats = getenv("NAV_TC_STATS") != nullptr;  // prints the re-rank volume (forces a sync)
+        unsigned long long evals = 0;
+        CU(bf_nn_tc((const double *)dev_points, n, (const double *)dev_queries, nq, (int *)dev_idx, (double *)dev_dist,
+                    sms, (cudaStream_t)cuda_stream, want_stats ? &evals : nullptr));
+        if (want_stats)
+            fprintf(stderr, "nav_bruteforce_nn_batch_dev[tensor cores]: n=%zu nq=%zu exact re-rank evaluations=%llu (%.1f per query)\n",
+                    n, nq, evals, nq ? (double)evals / (double)nq : 0.0);
+        return 0;
+    }
     CU(bf_nn((const double *)dev_points, n, (const double *)dev_queries, nq, (int *)dev_idx, (double *)dev_dist,
              (cudaStream_t)cuda_stream));
     return 0;

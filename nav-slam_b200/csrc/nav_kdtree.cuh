@@ -19,4 +19,9 @@ cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const d
 cudaError_t bf_nn(const double *d_pts, size_t n, const double *d_queries, size_t nq, int *d_idx, double *d_dist,
                   cudaStream_t stream);
 
+// tensor-core candidate tiles + exact re-rank (bf_tc.cu); *h_evals_out (optional, forces a stream sync)
+// receives the number of exact distance evaluations the re-rank needed
+cudaError_t bf_nn_tc(const double *d_pts, size_t n, const double *d_queries, size_t nq, int *d_idx, double *d_dist,
+                     int sm_count, cudaStream_t stream, unsigned long long *h_evals_out);
+
 }  // namespace nav

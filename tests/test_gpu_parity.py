@@ -433,6 +433,45 @@ def test_kdtree_1m_vs_bruteforce(pkg, oracle, synth):
         tree.close()
 
 
+@pytest.mark.parametrize("kind", ["uniform", "clustered", "integer", "duplicates", "offset", "line", "special"])
+@pytest.mark.parametrize("n,nq", [(1, 5), (31, 200), (256, 128), (1000, 777), (5000, 4096)])
+def test_bruteforce_tensor_cores_exact(pkg, oracle, synth, kind, n, nq):
+    """tcgen05 candidate tiles + exact re-rank (bf_tc.cu) must give the canonical exact answer on
+    every input: same idx (lowest index on ties) and bit-identical distance as the CPU oracle."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(n * 7 + nq)
+    if kind == "uniform":
+        pts = synth.map_points(n, seed=n)
+    elif kind == "clustered":
+        pts = synth.map_points(n, variant="clustered", seed=n)
+    elif kind == "integer":
+        pts = rng.integers(0, 30, size=(n, 3)).astype(np.float64)        # many exact ties
+    elif kind == "duplicates":
+        pts = np.repeat(rng.normal(0, 100, size=((n + 3) // 4, 3)), 4, axis=0)[:n]
+    elif kind == "offset":
+        pts = rng.normal(0, 20, size=(n, 3)) + np.array([3.0e7, -2.0e7, 1.0e7])  # dense, far from the origin
+    elif kind == "line":
+        pts = np.stack([np.arange(n, dtype=np.float64) * 0.001] * 3, axis=1) + 5.0e4
+    else:
+        pts = rng.normal(0, 100, size=(n, 3))
+        pts[0] = np.nan
+        if n > 3:
+            pts[2, 1] = np.inf
+    q = pts[rng.integers(0, n, size=nq)] + rng.normal(0, 3, size=(nq, 3))
+    q = np.nan_to_num(q, nan=1.0, posinf=2.0, neginf=-2.0)
+    if kind == "integer":
+        q = np.rint(q)
+    d_pts, d_q = torch.from_numpy(pts).cuda(), torch.from_numpy(q).cuda()
+    d_idx = torch.empty(nq, dtype=torch.int32, device="cuda")
+    d_dist = torch.empty(nq, dtype=torch.float64, device="cuda")
+    pkg.bruteforce_nn_dev(0, d_pts.data_ptr(), n, d_q.data_ptr(), nq, d_idx.data_ptr(), d_dist.data_ptr(),
+                          use_tensor_cores=True, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    oi, od = oracle.nn_brute(pts, q)
+    assert np.array_equal(d_idx.cpu().numpy(), oi)
+    assert np.array_equal(d_dist.cpu().numpy(), od)
+
+
 def test_no_device_errors_are_loud(pkg):
     with pytest.raises(pkg.NavError):
         pkg.Context(8, 8, device=99)
