@@ -93,8 +93,11 @@ int nav_kdtree_nn_batch(nav_kdtree *tree, const nav_point *queries, size_t nq,
                         int32_t *idx_out, double *dist_out, nav_point *nearest_out);
 int nav_kdtree_nn_batch_dev(nav_kdtree *tree, const void *dev_queries, size_t nq,
                             void *dev_idx_out, void *dev_dist_out, void *cuda_stream);
-/* exact brute-force baseline on the same contract (tensor-core candidate tiles + exact re-rank
- * when use_tensor_cores != 0, plain fp64 scan otherwise) */
+/* exact brute force on the same contract.  use_tensor_cores == 0: plain binary64 scan.
+ * use_tensor_cores != 0: tcgen05 candidate tiles (bf16 hi/mid/lo splits, fp32 accumulate in TMEM) flag
+ * every 32-point group that can contain the nearest neighbour, then an exact binary64 re-rank of the
+ * flagged groups; same answers for any input.  Measured on B200 it beats the fp64 scan from ~4 K
+ * points but never the kd-tree (profiles/README.md), so nothing selects it automatically. */
 int nav_bruteforce_nn_batch_dev(int device, const void *dev_points, size_t n, const void *dev_queries,
                                 size_t nq, void *dev_idx_out, void *dev_dist_out,
                                 int use_tensor_cores, void *cuda_stream);

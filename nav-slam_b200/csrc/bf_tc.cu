@@ -24,6 +24,7 @@
 // The answer is therefore exact for any input; only the run time depends on how many groups survive
 // (dense maps far from their centre flag many).  profiles/README.md records where this beats the tree.
 #include <cuda_bf16.h>
+#include <limits.h>
 #include <math.h>
 #include <stdint.h>
 
@@ -350,44 +351,66 @@ k_tc_tiles(const __nv_bfloat16 *__restrict__ aop, const __nv_bfloat16 *__restric
     }
 }
 
-// exact re-rank: one thread per query, flagged groups in ascending index order, binary64 reference
-// arithmetic, strict '<' => lowest index among equal dsq
-__global__ void __launch_bounds__(128)
+// exact re-rank: one warp per query.  Lanes first fetch the flag bytes of 32 tiles at a time, then the
+// warp walks the flagged groups: lane l evaluates point l of the group (one coalesced 768-byte read)
+// with the reference's binary64 arithmetic, and a lexicographic (dsq, index) min-reduction keeps the
+// lowest index among equal dsq.
+__global__ void __launch_bounds__(256)
 k_tc_rerank(const double *__restrict__ pts, long long n, const double *__restrict__ queries, long long nq,
             long long nq_pad, int n_tiles, const unsigned char *__restrict__ group_mask,
             const unsigned long long *__restrict__ stats, int *__restrict__ idx_out, double *__restrict__ dist_out,
             unsigned long long *__restrict__ n_evals) {
-    const long long qi = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long qi = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (qi >= nq) return;
     const double qx = queries[qi * 3], qy = queries[qi * 3 + 1], qz = queries[qi * 3 + 2];
     double best = INFINITY;
-    int bidx = -1;
+    int bidx = INT_MAX;
     unsigned evals = 0;
     // infinite coordinates make the centred operands meaningless: then every group is re-ranked
     double c[3], pmax;
     centre_of(stats, c, pmax);
     const double qmax = stats[6] ? okey_inv(stats[6]) : 0.0;
     const bool scan_all = !(pmax < INFINITY) || !(qmax < INFINITY) || !(fabs(c[0]) + fabs(c[1]) + fabs(c[2]) < INFINITY);
-    for (int t = 0; t < n_tiles; ++t) {
-        unsigned m = scan_all ? 0xffu : group_mask[(size_t)t * nq_pad + qi];
-        while (m) {
-            const int g = __ffs(m) - 1;
-            m &= m - 1;
-            const long long j0 = (long long)t * kTcN + g * kTcGroup;
-            const long long j1 = min(n, j0 + kTcGroup);
-            for (long long j = j0; j < j1; ++j) {
-                const double d = dsq3(dsub(pts[j * 3], qx), dsub(pts[j * 3 + 1], qy), dsub(pts[j * 3 + 2], qz));
-                if (d < best) {
-                    best = d;
-                    bidx = (int)j;
+    for (int t0 = 0; t0 < n_tiles; t0 += 32) {
+        const int tl = t0 + lane;
+        unsigned mine = 0;
+        if (tl < n_tiles) mine = scan_all ? 0xffu : group_mask[(size_t)tl * nq_pad + qi];
+        unsigned any = __ballot_sync(0xffffffffu, mine != 0);
+        while (any) {
+            const int src = __ffs(any) - 1;
+            any &= any - 1;
+            unsigned m = __shfl_sync(0xffffffffu, mine, src);
+            while (m) {
+                const int g = __ffs(m) - 1;
+                m &= m - 1;
+                const long long j = (long long)(t0 + src) * kTcN + g * kTcGroup + lane;
+                if (j < n) {
+                    const double d = dsq3(dsub(pts[j * 3], qx), dsub(pts[j * 3 + 1], qy), dsub(pts[j * 3 + 2], qz));
+                    if (d < best || (d == best && (int)j < bidx)) {
+                        best = d;
+                        bidx = (int)j;
+                    }
                 }
+                evals += 1;
             }
-            evals += (unsigned)(j1 - j0);
         }
     }
-    idx_out[qi] = bidx;
-    dist_out[qi] = bidx >= 0 ? __dsqrt_rn(best) : INFINITY;
-    if (n_evals) atomicAdd(n_evals, (unsigned long long)evals);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, d);
+        if (ob < best || (ob == best && oi < bidx)) {
+            best = ob;
+            bidx = oi;
+        }
+    }
+    if (lane == 0) {
+        const bool found = best < INFINITY || bidx != INT_MAX;
+        idx_out[qi] = found && bidx != INT_MAX ? bidx : -1;
+        dist_out[qi] = found && bidx != INT_MAX ? __dsqrt_rn(best) : INFINITY;
+        if (n_evals) atomicAdd(n_evals, (unsigned long long)evals * kTcGroup);
+    }
 }
 
 __global__ void k_tc_init_stats(unsigned long long *stats) {
@@ -440,7 +463,7 @@ cudaError_t bf_nn_tc(const double *d_pts, size_t n, const double *d_queries, siz
         k_tc_prep_queries<<<g3, 128, 0, stream>>>(d_queries, (long long)nq, nq_pad, stats, aop);
         k_tc_tiles<1><<<(unsigned)q_tiles, kTcThreads, dyn, stream>>>(aop, bop, (int)n_tiles, nq_pad, stats, rowmax, mask);
         k_tc_tiles<2><<<(unsigned)q_tiles, kTcThreads, dyn, stream>>>(aop, bop, (int)n_tiles, nq_pad, stats, rowmax, mask);
-        k_tc_rerank<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(d_pts, (long long)n, d_queries, (long long)nq, nq_pad,
+        k_tc_rerank<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, stream>>>(d_pts, (long long)n, d_queries, (long long)nq, nq_pad,
                                                                       (int)n_tiles, mask, stats, d_idx, d_dist, stats + 8);
     }
     TC_CHECK(cudaGetLastError());
