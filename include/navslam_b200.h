@@ -135,6 +135,14 @@ int nav_frontend_frame(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos_
                        const nav_pos *pos_last, const nav_pos *pos_final, int *feature_out,
                        int32_t *nn_idx_out, double *nn_dist_out, nav_point *global_out);
 
+/* nav_frontend_frame for L5-type input: takes the depth matrix of
+ * utils/pointcloud.h:13-17 (int mm, rows x cols) instead of the cloud; convertToPointCloud
+ * (utils/pointcloud.c:8) runs on the device in front of the frame kernel, so 4 B/pixel cross PCIe
+ * instead of 24.  cloud_out (optional) receives the converted lidar-frame cloud. */
+int nav_frontend_frame_depth(nav_ctx *ctx, const int *distances, const nav_pos *pos_predict,
+                             const nav_pos *pos_last, const nav_pos *pos_final, nav_point *cloud_out,
+                             int *feature_out, int32_t *nn_idx_out, double *nn_dist_out, nav_point *global_out);
+
 /* Pipelined variant of nav_frontend_frame for streams of frames: returns immediately; the upload of
  * this frame, the kernels of the previous one and the downloads of the one before overlap on three
  * CUDA streams.  All host pointers must be pinned (nav_host_alloc / cudaHostRegister).  The outputs

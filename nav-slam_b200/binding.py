@@ -44,7 +44,7 @@ EXPORTS = [
     "nav_extract_feature_batch_dev", "nav_frontend_frame_dev", "nav_slam_init_dev",
     "nav_frame_results_dev", "nav_profile_enable", "nav_profile_read", "nav_row_map_export",
     "nav_exact_fallback_count", "nav_frontend_frame_async", "nav_frontend_wait",
-    "nav_frontend_sequence_dev", "nav_slam_localization_fast",
+    "nav_frontend_sequence_dev", "nav_slam_localization_fast", "nav_frontend_frame_depth",
 ]
 
 
@@ -110,6 +110,8 @@ def load_library(build_if_missing: bool = True):
     L.nav_frontend_frame_async.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
                                            vp, vp, vp, vp]
     L.nav_frontend_wait.argtypes = [vp]
+    L.nav_frontend_frame_depth.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
+                                           vp, vp, vp, vp, vp]
     L.nav_extract_feature_batch_dev.argtypes = [vp, vp, C.c_size_t, vp]
     L.nav_frontend_frame_dev.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos)]
     L.nav_frontend_sequence_dev.argtypes = [vp, vp, C.c_size_t, C.POINTER(NavPos), C.POINTER(NavPos),
@@ -261,6 +263,19 @@ class Context:
                                          _pos_array(pos_last, n), _pos_array(pos_final, n), feat.ctypes.data,
                                          idx.ctypes.data, dist.ctypes.data, g.ctypes.data), self.L)
         return feat, idx, dist, g
+
+    def frontend_frame_depth(self, distances, pos_predict, pos_last, pos_final):
+        d = np.ascontiguousarray(distances, dtype=np.int32).reshape(self.rows, self.cols)
+        shp = (self.rows, self.cols)
+        cloud = np.empty(shp + (3,))
+        feat = np.empty(shp, dtype=np.int32)
+        idx = np.empty(shp, dtype=np.int32)
+        dist = np.empty(shp)
+        g = np.empty(shp + (3,))
+        _check(self.L.nav_frontend_frame_depth(self.h, d.ctypes.data, _pos_array(pos_predict), _pos_array(pos_last),
+                                               _pos_array(pos_final), cloud.ctypes.data, feat.ctypes.data,
+                                               idx.ctypes.data, dist.ctypes.data, g.ctypes.data), self.L)
+        return cloud, feat, idx, dist, g
 
     def frontend_frame_async(self, cloud_ptr, pos_predict, pos_last, pos_final, feat_ptr, idx_ptr, dist_ptr,
                              global_ptr):

@@ -784,6 +784,31 @@ extern "C" int nav_frontend_frame(nav_ctx *c, const nav_point *cloud, const nav_
     return finish_call(c, "nav_frontend_frame");
 }
 
+// L5 ingest fused with the frame (device part): the depth matrix (4 B/pixel instead of the
+// 24 B/pixel cloud) is uploaded, converted on the device (a2) and fed straight to the frame kernel;
+// the converted lidar-frame cloud is returned only if the caller asks for it.
+extern "C" int nav_frontend_frame_depth(nav_ctx *c, const int *distances, const nav_pos *pos_predict,
+                                        const nav_pos *pos_last, const nav_pos *pos_final, nav_point *cloud_out,
+                                        int *feature_out, int32_t *nn_idx_out, double *nn_dist_out,
+                                        nav_point *global_out) {
+    CTX_ENTER(c, "nav_frontend_frame_depth");
+    if (!distances || !pos_predict || !pos_last || !pos_final) return fail("nav_frontend_frame_depth: null argument");
+    if (c->n_seq != 1) return fail("nav_frontend_frame_depth: needs n_seq == 1");
+    if (!c->have_map) return fail("nav_frontend_frame_depth: call nav_slam_init first");
+    if (c->stage.reserve(c->ntot * (4 + 24 + 24 + 4 + 4 + 8) + 4096, c->stream)) return fail("nav_frontend_frame_depth: staging");
+    if (c->stage.h2d(c->d_dist, distances, c->npx * 4, c->stream)) return fail("nav_frontend_frame_depth: H2D");
+    launch_convert(c->d_dist, c->d_tan_col, c->d_tan_row, c->d_cloud, c->rows, c->cols, c->sm_count, c->stream);
+    c->launches++;
+    run_frame_fused(c, c->d_cloud, c->d_labels, c->d_nn_idx, c->d_nn_dist, pos_predict, pos_last, pos_final);
+    c->cloud_resident = true;
+    if (cloud_out && c->stage.d2h(cloud_out, c->d_cloud, c->ntot * 24, c->stream)) return fail("nav_frontend_frame_depth: D2H");
+    if (feature_out && c->stage.d2h(feature_out, c->d_labels, c->ntot * 4, c->stream)) return fail("nav_frontend_frame_depth: D2H");
+    if (nn_idx_out && c->stage.d2h(nn_idx_out, c->d_nn_idx, c->ntot * 4, c->stream)) return fail("nav_frontend_frame_depth: D2H");
+    if (nn_dist_out && c->stage.d2h(nn_dist_out, c->d_nn_dist, c->ntot * 8, c->stream)) return fail("nav_frontend_frame_depth: D2H");
+    if (global_out && c->stage.d2h(global_out, c->map.pts, c->ntot * 24, c->stream)) return fail("nav_frontend_frame_depth: D2H");
+    return finish_call(c, "nav_frontend_frame_depth");
+}
+
 // ------------------------------------------------------------------ pipelined host path ------
 // Same work as nav_frontend_frame, but nothing blocks: frame t's upload (copy-in stream), frame
 // t-1's kernels (context stream) and frame t-2's downloads (copy-out stream) overlap, with two

@@ -560,7 +560,7 @@ cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const d
     // kernel wins up to ~1 M points (127 vs 137 us), the converged work-refilling kernel wins on
     // maps that no longer fit in L2 (10 M points: 199 vs 219 us); a short explicit stack is faster only
     // around 64 K points and slower at 10 M, so it stays opt-in.  NAV_KD_KERNEL = plain|conv|stack overrides.
-    const char *kk = getenv("NAV_KD_KERNEL");
+    static const char *kk = getenv("NAV_KD_KERNEL");  // read once
     const int use_stack = kk && !strcmp(kk, "stack");
     const bool use_conv = kk ? !strcmp(kk, "conv") : n >= ((size_t)1 << 22);
     if (!sort_queries && use_conv && d_counter && n > 0) {

@@ -181,13 +181,12 @@ void launch_labels(const double *cloud, int *labels, double *curv_or_null, long 
     const int tiles_per_row = div_up(cols, kTile);
     const long long n_tiles = n_rows * tiles_per_row;
     long long grid = (long long)sm_count * 8;
-    if (const char *e = getenv("NAV_LABELS_CTAS_PER_SM")) grid = (long long)sm_count * atoi(e);
     if (grid > n_tiles) grid = n_tiles;
     const long long n_pts = n_rows * (long long)cols;
     const long long n_tiles_1d = (n_pts + kTileOut - 1) / kTileOut;
     const bool tma_ok = cols >= 5 && (((uintptr_t)cloud) % 16 == 0) && n_tiles_1d >= 4LL * sm_count &&
                         n_pts < (1LL << 31);
-    if (tma_ok && !curv_or_null && !getenv("NAV_LABELS_CTAS_PER_SM")) {  // persistent: exactly one resident wave
+    if (tma_ok && !curv_or_null) {  // persistent: exactly one resident wave
         static int per_sm = 0;
         if (!per_sm && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_labels_tma, kTile, 0) != cudaSuccess)
             per_sm = 4;

@@ -226,6 +226,32 @@ def test_frontend_multi_sequence(pkg, oracle, synth):
         s.close()
 
 
+@pytest.mark.parametrize("shape", [(8, 8), (16, 1800)])
+def test_frontend_frame_from_depth(ctxs, oracle, synth, shape):
+    """8f #3: depth matrix in, convertToPointCloud fused in front of the frame kernel."""
+    r, c = shape
+    ctx = ctxs(shape)
+    slam = oracle.slam(r, c, 1)
+    rng = np.random.default_rng(4)
+    depth = [synth.l5_depth_frame(f, r, c) if shape == (8, 8) else
+             (3000 + 40 * np.sin(np.arange(c) / 9.0)[None, :] + rng.integers(-6, 7, size=(r, c)) - 15 * f).astype(np.int32)
+             for f in range(4)]
+    depth[2][0, :3] = 0  # invalid returns -> (0,0,0)
+    clouds = [oracle.convert(d) for d in depth]
+    z = np.zeros(6)
+    assert np.array_equal(ctx.slam_init(z, clouds[0]), slam.init(z, clouds[0]))
+    last = z
+    for f in range(1, 4):
+        pred = last + np.array([-14.0, 0.5, 0.0, 0.0, 0.0, 0.1])
+        final = last + np.array([-15.0, 0.0, 0.0, 0.0, 0.0, 0.0])
+        cloud, feat, idx, dist, g = ctx.frontend_frame_depth(depth[f], pred, last, final)
+        ofeat, oidx, odist, og = slam.frontend_frame(clouds[f], pred, last, final)
+        assert np.array_equal(cloud, clouds[f]) and np.array_equal(feat, ofeat)
+        assert np.array_equal(idx, oidx) and np.array_equal(dist, odist) and np.array_equal(g, og)
+        last = final
+    slam.close()
+
+
 def test_frontend_async_pipeline_matches_sync(pkg, oracle, synth):
     """nav_frontend_frame_async (three overlapping streams, two slots) returns what the blocking call
     returns, frame for frame."""
