@@ -154,6 +154,24 @@ int nav_frontend_frame_async(nav_ctx *ctx, const nav_point *cloud, const nav_pos
                              int32_t *nn_idx_out, double *nn_dist_out, nav_point *global_out);
 int nav_frontend_wait(nav_ctx *ctx);
 
+/* ---- data formats either side of the path (host code) ----------------- */
+/* replaces L9_LidarProcessData (src/main.c:77-128): parses "frame,row,col,x,y,z,conf" records after one
+ * header line into frames_out[max_frames][rows][cols] (use nav_host_alloc memory to make the frames a
+ * DMA source); a change of the frame number starts the next frame; records outside the image are
+ * skipped.  Pixels that no record names keep whatever frames_out held (the reference leaves its stack
+ * array uninitialised there).  Same values as fscanf("%lf") bit for bit. */
+int nav_l9_csv_read(const char *path, int rows, int cols, size_t max_frames, nav_point *frames_out,
+                    int *timestamps_out, size_t *n_frames_out);
+/* the header line of point_cloud_data.csv (src/main.c:243) */
+const char *nav_csv_header(void);
+/* replaces the per-frame fprintf loop of src/main.c:320-352 (L5) / :433-464 (L9): rows*cols lines
+ * "%zu,%d,%d,%.2f,%.2f,%.2f,%d" + 18 pose columns "%.2f", byte-identical to glibc's printf.
+ * distances / imu / ekf_pos may be NULL (printed as 0 / 0.00).  Returns the bytes written, 0 if cap is
+ * too small (340 B per line always suffices for finite data below 1e300). */
+size_t nav_csv_format_frame(char *buf, size_t cap, unsigned long long timestamp, int rows, int cols,
+                            const nav_point *global_cloud, const int *distances, const double imu[6],
+                            const nav_pos *lidar_pos, const nav_pos *ekf_pos);
+
 /* ---- device-resident entry points (inputs already in HBM) ------------------------------ */
 /* labels for n_images images [n_images][rows][cols] in one launch (pose independent) */
 int nav_extract_feature_batch_dev(nav_ctx *ctx, const void *dev_clouds, size_t n_images,

@@ -11,5 +11,5 @@ Layout:
 The directory name has a hyphen, so import it with importlib.import_module("nav-slam_b200").
 """
 from . import build, synth  # noqa: F401
-from .binding import (Context, KdTree, NavError, bruteforce_nn_dev, device_count,  # noqa: F401
-                      load_library)
+from .binding import (Context, KdTree, NavError, bruteforce_nn_dev, csv_format_frame,  # noqa: F401
+                      device_count, l9_csv_read, load_library)

@@ -110,6 +110,11 @@ def load_library(build_if_missing: bool = True):
     L.nav_frontend_frame_async.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
                                            vp, vp, vp, vp]
     L.nav_frontend_wait.argtypes = [vp]
+    L.nav_l9_csv_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_size_t, vp, vp, C.POINTER(C.c_size_t)]
+    L.nav_csv_header.restype = C.c_char_p
+    L.nav_csv_format_frame.restype = C.c_size_t
+    L.nav_csv_format_frame.argtypes = [vp, C.c_size_t, C.c_ulonglong, C.c_int, C.c_int, vp, vp, vp,
+                                       C.POINTER(NavPos), C.POINTER(NavPos)]
     L.nav_frontend_frame_depth.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
                                            vp, vp, vp, vp, vp]
     L.nav_extract_feature_batch_dev.argtypes = [vp, vp, C.c_size_t, vp]
@@ -401,6 +406,32 @@ def bruteforce_nn_dev(device, dev_pts_ptr, n, dev_q_ptr, nq, dev_idx_ptr, dev_di
     L = load_library()
     _check(L.nav_bruteforce_nn_batch_dev(device, dev_pts_ptr, n, dev_q_ptr, nq, dev_idx_ptr, dev_dist_ptr,
                                          1 if use_tensor_cores else 0, stream), L)
+
+
+def l9_csv_read(path, rows, cols, max_frames):
+    """nav_l9_csv_read: returns (frames [n,rows,cols,3] float64, timestamps [n] int32)."""
+    L = load_library()
+    frames = np.zeros((max_frames, rows, cols, 3))
+    ts = np.zeros(max_frames, dtype=np.int32)
+    n = C.c_size_t(0)
+    _check(L.nav_l9_csv_read(path.encode(), rows, cols, max_frames, frames.ctypes.data, ts.ctypes.data, C.byref(n)), L)
+    return frames[:n.value], ts[:n.value]
+
+
+def csv_format_frame(timestamp, global_cloud, lidar_pos, distances=None, imu=None, ekf_pos=None) -> bytes:
+    """nav_csv_format_frame: the rows*cols CSV lines of one frame (src/main.c:320-352)."""
+    L = load_library()
+    g = _pts(global_cloud)
+    rows, cols = g.shape[0], g.shape[1]
+    buf = C.create_string_buffer(rows * cols * 400 + 1024)
+    d = np.ascontiguousarray(distances, dtype=np.int32) if distances is not None else None
+    im = np.ascontiguousarray(imu, dtype=np.float64) if imu is not None else None
+    n = L.nav_csv_format_frame(buf, len(buf), int(timestamp), rows, cols, g.ctypes.data,
+                               d.ctypes.data if d is not None else None, im.ctypes.data if im is not None else None,
+                               _pos_array(lidar_pos), _pos_array(ekf_pos) if ekf_pos is not None else None)
+    if n == 0:
+        raise NavError("nav_csv_format_frame: buffer too small")
+    return buf.raw[:n]
 
 
 def device_count() -> int:

@@ -27,6 +27,15 @@ static int fail(const char *fmt, ...) {
     return 1;
 }
 
+// error channel for the other translation units of the library (io.cu)
+int nav_io_fail(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
 #define CU(call)                                                                              \
     do {                                                                                      \
         cudaError_t e_ = (call);                                                              \

@@ -6,7 +6,7 @@
 # per-shape header / slam.c variants are produced with sed into a mktemp
 # directory that is deleted when the script exits.
 #
-#   libnavref_<RxC>.so : slam.c + kdtree.c + pointcloud.c + ekf.c + oracle/ref_driver.c
+#   libnavref_<RxC>.so : slam.c + kdtree.c + pointcloud.c + ekf.c + main.c (main renamed) + oracle/ref_driver.c
 #                        8x8 is built from the untouched sources.  Other shapes
 #                        rewrite ONLY utils/pointcloud.h:9-10 (MAX_ROWS/MAX_COLS,
 #                        unconditional #defines) and the two fixed
@@ -51,12 +51,14 @@ for shape in $SHAPES; do
         # the include guard POINTCLOUD_H makes every later #include "pointcloud.h" a no-op
         pre="-include $st/pointcloud.h"
     fi
-    $CC $CFLAGS -shared $pre $inc "$slam" "$REF/utils/kdtree.c" "$REF/utils/pointcloud.c" \
-        "$REF/src/ekf.c" "$HERE/ref_driver.c" -lm -o "$OUT/libnavref_$shape.so"
     # objects of the caller side (main.c, ekf.c) for linking against the B200 shim
     $CC $CFLAGS $pre $inc -I"$HERE/jansson_compat" -c "$REF/src/main.c" -o "$OUT/obj/main_$shape.o"
     $CC $CFLAGS $pre $inc -Dmain=ref_main -I"$HERE/jansson_compat" -c "$REF/src/main.c" -o "$OUT/obj/main_nomain_$shape.o"
     $CC $CFLAGS $pre $inc -c "$REF/src/ekf.c" -o "$OUT/obj/ekf_$shape.o"
+    # the library also carries main.c (as ref_main) so that its CSV reader L9_LidarProcessData is callable
+    $CC $CFLAGS -shared $pre $inc "$slam" "$REF/utils/kdtree.c" "$REF/utils/pointcloud.c" \
+        "$REF/src/ekf.c" "$OUT/obj/main_nomain_$shape.o" "$HERE/ref_driver.c" -lm -l:libjansson.so.4 \
+        -o "$OUT/libnavref_$shape.so"
     # whole-program reference binaries
     $CC $CFLAGS $pre $inc "$OUT/obj/main_$shape.o" "$OUT/obj/ekf_$shape.o" "$slam" \
         "$REF/utils/kdtree.c" "$REF/utils/pointcloud.c" -lm -l:libjansson.so.4 -o "$OUT/navref_main_$shape"

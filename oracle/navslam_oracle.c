@@ -10,6 +10,7 @@
  */
 #include "navslam_oracle.h"
 
+#include <stdio.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -506,4 +507,68 @@ void nso_frontend_frame(nso_slam *s, const nso_point *cloud, const nso_pos *pos_
     }
     if (feature_out) memcpy(feature_out, s->feature, n * sizeof(int));
     map_frame(s, pos_final, cloud, global_out);
+}
+
+/* ---------------------------------------------------------------- caller-side data formats ---- */
+/* src/main.c:77-128 */
+int nso_l9_csv_read(const char *path, int rows, int cols, size_t max_frames, nso_point *frames,
+                    int32_t *timestamps, size_t *n_frames) {
+    FILE *fp = fopen(path, "r");
+    *n_frames = 0;
+    if (!fp) return 1;
+    char header[256];
+    if (!fgets(header, sizeof(header), fp)) { /* main.c:87-91 */
+        fclose(fp);
+        return 0;
+    }
+    int frame, row, col, conf, current = -1;
+    double x, y, z;
+    size_t count = 0;
+    while (fscanf(fp, "%d,%d,%d,%lf,%lf,%lf,%d", &frame, &row, &col, &x, &y, &z, &conf) == 7) { /* main.c:99 */
+        /* main.c:100 accepts col == MAX_COLS (one past the row); that write is out of bounds, so the
+         * restatement skips it like every other out-of-range record */
+        if (row < 0 || row >= rows || col < 0 || col >= cols) continue;
+        if (frame != current) { /* main.c:105-112 */
+            if (current != -1) count++;
+            if (count >= max_frames) {
+                fclose(fp);
+                *n_frames = max_frames;
+                return 2;
+            }
+            current = frame;
+            if (timestamps) timestamps[count] = frame;
+        }
+        nso_point *d = &frames[count * (size_t)rows * cols + (size_t)row * cols + col];
+        d->x = x; /* main.c:115-117 */
+        d->y = y;
+        d->z = z;
+    }
+    *n_frames = current != -1 ? count + 1 : 0; /* main.c:121-125 */
+    fclose(fp);
+    return 0;
+}
+
+/* src/main.c:320-352 (the L5 handler passes doubles to every %.2f) */
+size_t nso_csv_format_frame(char *buf, size_t cap, unsigned long long timestamp, int rows, int cols,
+                            const nso_point *g, const int32_t *distances, const double *imu6,
+                            const nso_pos *lp, const nso_pos *ep) {
+    static const double zero6[6] = {0, 0, 0, 0, 0, 0};
+    const double *im = imu6 ? imu6 : zero6;
+    const nso_pos zp = {0, 0, 0, 0, 0, 0};
+    if (!ep) ep = &zp;
+    size_t off = 0;
+    for (int row = 0; row < rows; ++row)
+        for (int col = 0; col < cols; ++col) {
+            const nso_point *p = &g[(size_t)row * cols + col];
+            int n = snprintf(buf + off, cap - off,
+                             "%zu,%d,%d,%.2f,%.2f,%.2f,%d,%.2f,%.2f,%.2f,%.2f,%.2f,%.2f,%.2f,%.2f,%.2f,%.2f,%.2f,%.2f,"
+                             "%.2f,%.2f,%.2f,%.2f,%.2f,%.2f\n",
+                             (size_t)timestamp, row, col, p->x, p->y, p->z,
+                             distances ? (int)distances[(size_t)row * cols + col] : 0, im[0], im[1], im[2], im[3],
+                             im[4], im[5], lp->x, lp->y, lp->z, lp->roll, lp->pitch, lp->yaw, ep->x, ep->y, ep->z,
+                             ep->roll, ep->pitch, ep->yaw);
+            if (n < 0 || (size_t)n >= cap - off) return 0;
+            off += (size_t)n;
+        }
+    return off;
 }

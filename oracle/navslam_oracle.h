@@ -80,6 +80,16 @@ void nso_frontend_frame(nso_slam *s, const nso_point *cloud, const nso_pos *pos_
                         const nso_pos *pos_last, const nso_pos *pos_final,
                         int *feature_out, int32_t *nn_idx, double *nn_dist, nso_point *global_out);
 
+/* ---- caller-side data formats ------------------------------------------
+ * nso_l9_csv_read restates L9_LidarProcessData (src/main.c:77-128) with the C library's own fscanf;
+ * nso_csv_format_frame restates the fprintf loop of src/main.c:320-352 with snprintf.  Both are the
+ * checkers for nav_l9_csv_read / nav_csv_format_frame. */
+int nso_l9_csv_read(const char *path, int rows, int cols, size_t max_frames, nso_point *frames,
+                    int32_t *timestamps, size_t *n_frames);
+size_t nso_csv_format_frame(char *buf, size_t cap, unsigned long long timestamp, int rows, int cols,
+                            const nso_point *global_cloud, const int32_t *distances, const double *imu6,
+                            const nso_pos *lidar_pos, const nso_pos *ekf_pos);
+
 #ifdef __cplusplus
 }
 #endif

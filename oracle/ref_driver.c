@@ -129,3 +129,14 @@ static size_t dump_rec(KDNode *node, int depth, Point *out_pt, int *out_depth, s
 size_t refdrv_tree_preorder(KDNode *root, Point *out_pt, int *out_depth, size_t cap) {
     return dump_rec(root, 0, out_pt, out_depth, 0, cap);
 }
+
+/* ---- the caller-side data formats: the reference's own L9 CSV reader --------------
+ * L9_LidarProcessData (src/main.c:77-128) lives in main.c, which build_ref.sh links into this library
+ * with main renamed.  Returns the seconds the call took. */
+void L9_LidarProcessData(const char *filename, PointCloud *lidarData, size_t *lidarCount);
+
+double refdrv_l9_read(const char *path, PointCloud *frames, size_t *count) {
+    double t0 = now_s();
+    L9_LidarProcessData(path, frames, count);
+    return now_s() - t0;
+}

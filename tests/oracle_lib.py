@@ -103,6 +103,36 @@ class Oracle:
         L.nso_frontend_frame.argtypes = [C.c_void_p, c_double_p, C.POINTER(Pos), C.POINTER(Pos),
                                          C.POINTER(Pos), c_int_p, c_i32_p, c_double_p, c_double_p]
 
+        L.nso_l9_csv_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p,
+                                      C.POINTER(C.c_size_t)]
+        L.nso_csv_format_frame.restype = C.c_size_t
+        L.nso_csv_format_frame.argtypes = [C.c_void_p, C.c_size_t, C.c_ulonglong, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.POINTER(Pos), C.POINTER(Pos)]
+
+    # --- caller-side data formats
+    def l9_csv_read(self, path, rows, cols, max_frames):
+        frames = np.zeros((max_frames, rows, cols, 3))
+        ts = np.zeros(max_frames, dtype=np.int32)
+        n = C.c_size_t(0)
+        rc = self.lib.nso_l9_csv_read(path.encode(), rows, cols, max_frames, frames.ctypes.data, ts.ctypes.data,
+                                      C.byref(n))
+        return rc, frames[:n.value], ts[:n.value]
+
+    def csv_format_frame(self, timestamp, g, lidar_pos, distances=None, imu=None, ekf_pos=None) -> bytes:
+        g = _pts(g)
+        rows, cols = g.shape[0], g.shape[1]
+        buf = C.create_string_buffer(rows * cols * 25 * 330 + 1024)
+        d = np.ascontiguousarray(distances, dtype=np.int32) if distances is not None else None
+        im = np.ascontiguousarray(imu, dtype=np.float64) if imu is not None else None
+        lp = Pos.of(lidar_pos)
+        ep = Pos.of(ekf_pos) if ekf_pos is not None else None
+        n = self.lib.nso_csv_format_frame(buf, len(buf), int(timestamp), rows, cols, g.ctypes.data,
+                                          d.ctypes.data if d is not None else None,
+                                          im.ctypes.data if im is not None else None, C.byref(lp),
+                                          C.byref(ep) if ep is not None else None)
+        assert n > 0
+        return buf.raw[:n]
+
     # --- function level
     def convert(self, dist):
         dist = np.ascontiguousarray(dist, dtype=np.int32)
@@ -289,8 +319,20 @@ class RefLib:
         L.slam_mapping.argtypes = [C.c_void_p, Pos, C.c_void_p]
         L.slam_localization.restype = Pos
         L.slam_localization.argtypes = [C.c_void_p, C.c_void_p, Pos, Pos]
+        L.refdrv_l9_read.restype = C.c_double
+        L.refdrv_l9_read.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(C.c_size_t)]
         self.sizeof_pointcloud = L.refdrv_sizeof_pointcloud()
         self.sizeof_slam_attr = L.refdrv_sizeof_slam_attr()
+
+    def l9_csv_read(self, path, max_frames):
+        """The reference's own L9_LidarProcessData into zeroed PointCloud structs.
+        Returns (frames [n,R,C,3], timestamps [n], seconds)."""
+        buf = np.zeros((max_frames, self.sizeof_pointcloud), dtype=np.uint8)
+        n = C.c_size_t(0)
+        secs = self.lib.refdrv_l9_read(path.encode(), buf.ctypes.data, C.byref(n))
+        ts = buf[:n.value, :4].copy().view(np.int32).reshape(-1)
+        pts = buf[:n.value, 8:].copy().view(np.float64).reshape(n.value, self.rows, self.cols, 3)
+        return pts, ts, secs
 
     # PointCloud = {int ts; Point pts[R][C]} with the points at byte offset 8
     def pack_cloud(self, cloud, ts=0) -> np.ndarray:
