@@ -45,6 +45,7 @@ EXPORTS = [
     "nav_frame_results_dev", "nav_profile_enable", "nav_profile_read", "nav_row_map_export",
     "nav_exact_fallback_count", "nav_frontend_frame_async", "nav_frontend_wait",
     "nav_frontend_sequence_dev", "nav_slam_localization_fast", "nav_frontend_frame_depth",
+    "nav_l9_csv_read", "nav_csv_header", "nav_csv_format_frame",
 ]
 
 
