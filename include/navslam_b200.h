@@ -172,6 +172,22 @@ size_t nav_csv_format_frame(char *buf, size_t cap, unsigned long long timestamp,
                             const nav_point *global_cloud, const int *distances, const double imu[6],
                             const nav_pos *lidar_pos, const nav_pos *ekf_pos);
 
+/* The same text produced on the GPU (three small kernels: line lengths, prefix sum, format into shared
+ * memory + coalesced store).  global_cloud == NULL formats the context's resident global cloud of the
+ * frame mapped last (no upload at all); distances == NULL prints 0.  buf should be pinned memory
+ * (nav_host_alloc).  Frames holding inf / nan / |v| >= 2^57 are formatted by nav_csv_format_frame on
+ * the host instead -- identical bytes either way.  Returns 0 and *n_bytes_out, 1 on failure. */
+int nav_csv_format_frame_gpu(nav_ctx *ctx, unsigned long long timestamp, const nav_point *global_cloud,
+                             const int *distances, const double imu[6], const nav_pos *lidar_pos,
+                             const nav_pos *ekf_pos, char *buf, size_t cap, size_t *n_bytes_out);
+/* Device-resident variant: d_global_cloud (NULL = resident cloud), d_distances (NULL = 0) and d_text are
+ * device pointers; cap >= rows*cols*(124 + length of the 18 pose columns) (rows*cols*604 always
+ * suffices).  Synchronises the context's stream to report *n_bytes_out.  Returns 2 when the frame
+ * needs the host formatter (see above); d_text is then undefined. */
+int nav_csv_format_frame_dev(nav_ctx *ctx, unsigned long long timestamp, const nav_point *d_global_cloud,
+                             const int *d_distances, const double imu[6], const nav_pos *lidar_pos,
+                             const nav_pos *ekf_pos, char *d_text, size_t cap, size_t *n_bytes_out);
+
 /* ---- device-resident entry points (inputs already in HBM) ------------------------------ */
 /* labels for n_images images [n_images][rows][cols] in one launch (pose independent) */
 int nav_extract_feature_batch_dev(nav_ctx *ctx, const void *dev_clouds, size_t n_images,

@@ -45,7 +45,8 @@ EXPORTS = [
     "nav_frame_results_dev", "nav_profile_enable", "nav_profile_read", "nav_row_map_export",
     "nav_exact_fallback_count", "nav_frontend_frame_async", "nav_frontend_wait",
     "nav_frontend_sequence_dev", "nav_slam_localization_fast", "nav_frontend_frame_depth",
-    "nav_l9_csv_read", "nav_csv_header", "nav_csv_format_frame",
+    "nav_l9_csv_read", "nav_csv_header", "nav_csv_format_frame", "nav_csv_format_frame_gpu",
+    "nav_csv_format_frame_dev",
 ]
 
 
@@ -112,6 +113,9 @@ def load_library(build_if_missing: bool = True):
                                            vp, vp, vp, vp]
     L.nav_frontend_wait.argtypes = [vp]
     L.nav_l9_csv_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_size_t, vp, vp, C.POINTER(C.c_size_t)]
+    L.nav_csv_format_frame_gpu.argtypes = [vp, C.c_ulonglong, vp, vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), vp,
+                                           C.c_size_t, C.POINTER(C.c_size_t)]
+    L.nav_csv_format_frame_dev.argtypes = L.nav_csv_format_frame_gpu.argtypes
     L.nav_csv_header.restype = C.c_char_p
     L.nav_csv_format_frame.restype = C.c_size_t
     L.nav_csv_format_frame.argtypes = [vp, C.c_size_t, C.c_ulonglong, C.c_int, C.c_int, vp, vp, vp,
@@ -282,6 +286,28 @@ class Context:
                                                _pos_array(pos_final), cloud.ctypes.data, feat.ctypes.data,
                                                idx.ctypes.data, dist.ctypes.data, g.ctypes.data), self.L)
         return cloud, feat, idx, dist, g
+
+    def csv_rows(self, timestamp, lidar_pos, global_cloud=None, distances=None, imu=None, ekf_pos=None,
+                 out_ptr=None, out_cap=0) -> bytes:
+        """nav_csv_format_frame_gpu: the frame's CSV lines (src/main.c:320-352) formatted on the GPU.
+        global_cloud None = the resident global cloud of the frame mapped last.  out_ptr/out_cap: a pinned
+        host buffer to receive the text (then the return value is the byte count)."""
+        g = _pts(global_cloud) if global_cloud is not None else None
+        d = np.ascontiguousarray(distances, dtype=np.int32) if distances is not None else None
+        im = np.ascontiguousarray(imu, dtype=np.float64) if imu is not None else None
+        n = C.c_size_t(0)
+        if out_ptr is None:
+            cap = self.rows * self.cols * 700 + 1024
+            buf = C.create_string_buffer(cap)
+            ptr = C.addressof(buf)
+        else:
+            ptr, cap = out_ptr, out_cap
+        _check(self.L.nav_csv_format_frame_gpu(self.h, int(timestamp), g.ctypes.data if g is not None else None,
+                                               d.ctypes.data if d is not None else None,
+                                               im.ctypes.data if im is not None else None, _pos_array(lidar_pos),
+                                               _pos_array(ekf_pos) if ekf_pos is not None else None, ptr, cap,
+                                               C.byref(n)), self.L)
+        return buf.raw[:n.value] if out_ptr is None else n.value
 
     def frontend_frame_async(self, cloud_ptr, pos_predict, pos_last, pos_final, feat_ptr, idx_ptr, dist_ptr,
                              global_ptr):

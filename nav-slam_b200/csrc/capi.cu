@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "nav_kdtree.cuh"
+#include "csv_fixed2.cuh"
 #include "nav_kernels.cuh"
 
 using namespace nav;
@@ -183,6 +184,9 @@ struct nav_ctx {
     double *d_flat = nullptr;
     int *d_flat_count = nullptr;
     int *h_small = nullptr;  // pinned scratch for counts
+    char *d_csv = nullptr;   // device text of one frame's CSV rows (lazy)
+    void *d_csv_scratch = nullptr;
+    size_t csv_cap = 0;
     Stager stage;
     bool have_map = false, cloud_resident = false;
     uint64_t launches = 0;
@@ -272,6 +276,8 @@ extern "C" void nav_destroy(nav_ctx *c) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_small) cudaFreeHost(c->h_small);
+    if (c->d_csv) cudaFree(c->d_csv);
+    if (c->d_csv_scratch) cudaFree(c->d_csv_scratch);
     for (auto &sl : c->slots) {
         for (void *p : {(void *)sl.d_cloud, (void *)sl.d_labels})  // the other outputs live inside d_labels
             if (p) cudaFree(p);
@@ -816,6 +822,131 @@ extern "C" int nav_frontend_frame_depth(nav_ctx *c, const int *distances, const 
     if (nn_dist_out && c->stage.d2h(nn_dist_out, c->d_nn_dist, c->ntot * 8, c->stream)) return fail("nav_frontend_frame_depth: D2H");
     if (global_out && c->stage.d2h(global_out, c->map.pts, c->ntot * 24, c->stream)) return fail("nav_frontend_frame_depth: D2H");
     return finish_call(c, "nav_frontend_frame_depth");
+}
+
+
+// ------------------------------------------------------------------ CSV rows on the device ---
+// the text of src/main.c:320-352 for one frame, produced where the global cloud lives.
+namespace nav {
+size_t csv_pose_columns(char *out, const double imu[6], const nav_pos *lidar_pos, const nav_pos *ekf_pos);  // io.cu
+}
+
+static int csv_job(nav_ctx *c, const char *name, unsigned long long timestamp, const double *d_cloud,
+                   const int *d_dist, const double imu[6], const nav_pos *lp, const nav_pos *ep, CsvJob &job) {
+    char tail[18 * 340 + 4];
+    const size_t tail_len = csv_pose_columns(tail, imu, lp, ep);
+    if (tail_len > (size_t)kCsvTailMax) return -1;  // a pose column beyond 2^57 or not finite: host formatter
+    job.cloud = d_cloud;
+    job.dist = d_dist;
+    job.ts = timestamp;
+    job.n = (long long)c->npx;
+    job.cols = c->cols;
+    job.ts_len = dec_len(timestamp);
+    job.tail_len = (int)tail_len;
+    memcpy(job.tail, tail, tail_len);
+    if (!c->d_csv_scratch) {
+        if (cudaMalloc(&c->d_csv_scratch, csv_scratch_bytes((long long)c->npx)) != cudaSuccess)
+            return fail("%s: out of device memory", name);
+    }
+    return 0;
+}
+
+// Device-resident variant: d_global_cloud (NULL = the context's global cloud of the frame mapped last,
+// i.e. what nav_slam_mapping / nav_frontend_frame just produced) and d_distances (NULL = 0) are device
+// pointers, d_text receives the text; needs cap >= rows*cols*(124 + 18*23 + 1) unless the poses are
+// short.  *n_bytes_out is valid on return (the call synchronises the context's stream).  Returns 2
+// (and writes nothing useful) when some value needs the host formatter (inf, nan, |v| >= 2^57).
+extern "C" int nav_csv_format_frame_dev(nav_ctx *c, unsigned long long timestamp, const nav_point *d_global_cloud,
+                                        const int *d_distances, const double imu[6], const nav_pos *lidar_pos,
+                                        const nav_pos *ekf_pos, char *d_text, size_t cap, size_t *n_bytes_out) {
+    CTX_ENTER(c, "nav_csv_format_frame_dev");
+    if (!lidar_pos || !d_text || !n_bytes_out) return fail("nav_csv_format_frame_dev: null argument");
+    if (c->n_seq != 1) return fail("nav_csv_format_frame_dev: needs n_seq == 1");
+    if (!d_global_cloud && !c->have_map) return fail("nav_csv_format_frame_dev: no frame has been mapped yet");
+    CsvJob job;
+    const int rc = csv_job(c, "nav_csv_format_frame_dev", timestamp,
+                           d_global_cloud ? (const double *)d_global_cloud : c->map.pts, d_distances, imu, lidar_pos,
+                           ekf_pos, job);
+    if (rc > 0) return rc;
+    if (rc < 0) return 2;
+    if (cap < c->npx * (size_t)(kCsvHeadMax + job.tail_len)) return fail("nav_csv_format_frame_dev: d_text too small");
+    if (launch_csv_format(job, d_text, c->d_csv_scratch, c->stream)) return fail("nav_csv_format_frame_dev: launch failed");
+    c->launches += 3;
+    CU(cudaMemcpyAsync(c->h_small, c->d_csv_scratch, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *n_bytes_out = (size_t) * (unsigned long long *)c->h_small;
+    return ((unsigned *)c->h_small)[2] ? 2 : 0;
+}
+
+// Host-facing variant: the text lands in buf (pinned memory avoids a staging copy).  global_cloud
+// NULL = format the context's resident global cloud without any upload; distances NULL = 0.
+// Frames with values outside the device formatter's range are formatted by nav_csv_format_frame on
+// the host (same bytes).  Returns 0 and *n_bytes_out, or 1 (cap too small, CUDA failure).
+extern "C" int nav_csv_format_frame_gpu(nav_ctx *c, unsigned long long timestamp, const nav_point *global_cloud,
+                                        const int *distances, const double imu[6], const nav_pos *lidar_pos,
+                                        const nav_pos *ekf_pos, char *buf, size_t cap, size_t *n_bytes_out) {
+    CTX_ENTER(c, "nav_csv_format_frame_gpu");
+    if (!lidar_pos || !buf || !n_bytes_out) return fail("nav_csv_format_frame_gpu: null argument");
+    if (c->n_seq != 1) return fail("nav_csv_format_frame_gpu: needs n_seq == 1");
+    if (!global_cloud && !c->have_map) return fail("nav_csv_format_frame_gpu: no frame has been mapped yet");
+    *n_bytes_out = 0;
+    if (c->stage.reserve(c->npx * 28 + 4096, c->stream)) return fail("nav_csv_format_frame_gpu: staging");
+    const double *d_cloud = c->map.pts;
+    if (global_cloud) {
+        if (!c->d_global) CU(cudaMalloc((void **)&c->d_global, c->npx * 24));
+        if (c->stage.h2d(c->d_global, global_cloud, c->npx * 24, c->stream)) return fail("nav_csv_format_frame_gpu: H2D");
+        d_cloud = c->d_global;
+    }
+    if (distances && c->stage.h2d(c->d_dist, distances, c->npx * 4, c->stream)) return fail("nav_csv_format_frame_gpu: H2D");
+    CsvJob job;
+    int rc = csv_job(c, "nav_csv_format_frame_gpu", timestamp, d_cloud, distances ? c->d_dist : nullptr, imu, lidar_pos,
+                     ekf_pos, job);
+    if (rc > 0) return rc;
+    bool host_format = rc < 0;
+    if (!host_format) {
+        const size_t need = c->npx * (size_t)(kCsvHeadMax + job.tail_len);
+        if (need > c->csv_cap) {
+            CU(cudaStreamSynchronize(c->stream));
+            if (c->d_csv) cudaFree(c->d_csv);
+            c->d_csv = nullptr;
+            c->csv_cap = 0;
+            if (cudaMalloc((void **)&c->d_csv, need) != cudaSuccess) return fail("nav_csv_format_frame_gpu: out of device memory");
+            c->csv_cap = need;
+        }
+        if (launch_csv_format(job, c->d_csv, c->d_csv_scratch, c->stream)) return fail("nav_csv_format_frame_gpu: launch failed");
+        c->launches += 3;
+        CU(cudaMemcpyAsync(c->h_small, c->d_csv_scratch, 16, cudaMemcpyDeviceToHost, c->stream));
+        if (finish_call(c, "nav_csv_format_frame_gpu")) return 1;
+        const size_t total = (size_t) * (unsigned long long *)c->h_small;
+        host_format = ((unsigned *)c->h_small)[2] != 0;
+        if (!host_format) {
+            if (total > cap) return fail("nav_csv_format_frame_gpu: buf too small (%zu bytes needed)", total);
+            if (Stager::is_pinned(buf)) {
+                CU(cudaMemcpyAsync(buf, c->d_csv, total, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+            } else {
+                if (c->stage.reserve(total + 256, c->stream)) return fail("nav_csv_format_frame_gpu: staging");
+                if (c->stage.d2h(buf, c->d_csv, total, c->stream)) return fail("nav_csv_format_frame_gpu: D2H");
+                if (finish_call(c, "nav_csv_format_frame_gpu")) return 1;
+            }
+            *n_bytes_out = total;
+            return 0;
+        }
+    } else if (finish_call(c, "nav_csv_format_frame_gpu")) {
+        return 1;
+    }
+    // rare: inf / nan / |v| >= 2^57 somewhere in the frame -> the host writer prints the same bytes
+    std::vector<nav_point> tmp;
+    const nav_point *src = global_cloud;
+    if (!src) {
+        tmp.resize(c->npx);
+        CU(cudaMemcpy(tmp.data(), c->map.pts, c->npx * 24, cudaMemcpyDeviceToHost));
+        src = tmp.data();
+    }
+    const size_t n = nav_csv_format_frame(buf, cap, timestamp, c->rows, c->cols, src, distances, imu, lidar_pos, ekf_pos);
+    if (n == 0) return fail("nav_csv_format_frame_gpu: buf too small");
+    *n_bytes_out = n;
+    return 0;
 }
 
 // ------------------------------------------------------------------ pipelined host path ------

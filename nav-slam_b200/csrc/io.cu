@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/navslam_b200.h"
+#include "csv_fixed2.cuh"
 
 extern "C" const char *nav_last_error(void);
 int nav_io_fail(const char *fmt, ...);  // defined in capi.cu (sets the thread-local error)
@@ -167,100 +168,26 @@ extern "C" int nav_l9_csv_read(const char *path, int rows, int cols, size_t max_
 // ---------------------------------------------------------------------------------- writer -----
 namespace {
 
-// printf("%.2f") of a finite double, exactly: round-half-even of the binary value times 100,
-// computed with integers (what glibc's correctly rounded conversion prints)
+// printf("%.2f") of any double: the integer path of csv_fixed2.cuh, the C library for inf / nan / >= 2^57
 inline char *fmt_fixed2(char *o, double v) {
-    uint64_t bits;
-    memcpy(&bits, &v, 8);
-    if (bits >> 63) *o++ = '-';
-    const int ex = (int)((bits >> 52) & 0x7ff);
-    uint64_t m = bits & 0xfffffffffffffull;
-    if (ex == 0x7ff) {  // glibc: "inf" / "nan" ("-" already written for negative ones)
-        memcpy(o, m ? "nan" : "inf", 3);
-        return o + 3;
-    }
-    int e;  // value = m * 2^e
-    if (ex == 0) {
-        e = -1074;
-    } else {
-        m |= 1ull << 52;
-        e = ex - 1075;
-    }
-    uint64_t q;  // round(|v| * 100)
-    if (e >= 0) {
-        if (e > 4) {  // >= 2^57: beyond 64-bit scaled arithmetic, rare enough for the C library
-            char tmp[400];
-            const int n = snprintf(tmp, sizeof(tmp), "%.2f", fabs(v));
-            memcpy(o, tmp, (size_t)n);
-            return o + n;
-        }
-        q = (m << e) * 100ull;
-    } else {
-        const int k = -e;
-        const unsigned __int128 prod = (unsigned __int128)m * 100u;
-        if (k >= 120) {
-            q = 0;
-        } else {
-            const unsigned __int128 one = (unsigned __int128)1 << k;
-            unsigned __int128 quo = prod >> k;
-            const unsigned __int128 rem = prod & (one - 1), half = one >> 1;
-            if (rem > half || (rem == half && (quo & 1))) ++quo;
-            q = (uint64_t)quo;
-        }
-    }
-    const uint64_t ip = q / 100;
-    const unsigned fr = (unsigned)(q % 100);
-    char tmp[24];
-    int n = 0;
-    uint64_t t = ip;
-    do {
-        tmp[n++] = (char)('0' + t % 10);
-        t /= 10;
-    } while (t);
-    while (n) *o++ = tmp[--n];
-    *o++ = '.';
-    *o++ = (char)('0' + fr / 10);
-    *o++ = (char)('0' + fr % 10);
-    return o;
+    bool neg;
+    unsigned long long q;
+    if (nav::fixed2_scaled(v, neg, q)) return nav::put_fixed2(o, neg, q);
+    char tmp[400];
+    const int n = snprintf(tmp, sizeof(tmp), "%.2f", v);
+    memcpy(o, tmp, (size_t)n);
+    return o + n;
 }
 
-inline char *fmt_uint(char *o, unsigned long long v) {
-    char tmp[24];
-    int n = 0;
-    do {
-        tmp[n++] = (char)('0' + v % 10);
-        v /= 10;
-    } while (v);
-    while (n) *o++ = tmp[--n];
-    return o;
-}
-inline char *fmt_int(char *o, long long v) {
-    if (v < 0) {
-        *o++ = '-';
-        return fmt_uint(o, (unsigned long long)(-v));
-    }
-    return fmt_uint(o, (unsigned long long)v);
-}
+inline char *fmt_uint(char *o, unsigned long long v) { return nav::put_uint(o, v, nav::dec_len(v)); }
+inline char *fmt_int(char *o, long long v) { return nav::put_int(o, v); }
 
 }  // namespace
 
-extern "C" const char *nav_csv_header(void) {
-    // src/main.c:243
-    return "Timestamp,Row,Col,x,y,z,distance,IMU_x,IMU_y,IMU_z,IMU_roll,IMU_pitch,IMU_yaw,LiDAR_x,LiDAR_y,LiDAR_z,"
-           "LiDAR_roll,LiDAR_pitch,LiDAR_yaw,EKF_x,EKF_y,EKF_z,EKF_roll,EKF_pitch,EKF_yaw\n";
-}
-
-// One frame = rows*cols lines of src/main.c:324-349.  distances == NULL prints 0 (the L9 handler,
-// main.c:437-461); imu == NULL prints 0 for the six IMU columns and ekf == NULL prints 0 for the six EKF
-// columns, as integers like the reference's literal 0 arguments would... which the reference passes to
-// %.2f (undefined); both handlers' defined behaviour is reproduced: L5 passes doubles everywhere.
-extern "C" size_t nav_csv_format_frame(char *buf, size_t cap, unsigned long long timestamp, int rows, int cols,
-                                       const nav_point *global_cloud, const int *distances, const double imu[6],
-                                       const nav_pos *lidar_pos, const nav_pos *ekf_pos) {
-    if (!buf || !global_cloud || !lidar_pos || rows < 1 || cols < 1) return 0;
-    // the 18 pose columns are the same text on every line of the frame
-    char tail[18 * 340 + 4];
-    char *t = tail;
+namespace nav {
+// ",%.2f" x 18 + "\n" (src/main.c:331-348); out needs 18 * 340 + 2 bytes for arbitrary doubles
+size_t csv_pose_columns(char *out, const double imu[6], const nav_pos *lidar_pos, const nav_pos *ekf_pos) {
+    char *t = out;
     const double zero6[6] = {0, 0, 0, 0, 0, 0};
     const double *im = imu ? imu : zero6;
     for (int i = 0; i < 6; ++i) {
@@ -279,28 +206,51 @@ extern "C" size_t nav_csv_format_frame(char *buf, size_t cap, unsigned long long
         t = fmt_fixed2(t, ep[i]);
     }
     *t++ = '\n';
-    const size_t tail_len = (size_t)(t - tail);
+    return (size_t)(t - out);
+}
+}  // namespace nav
+
+extern "C" const char *nav_csv_header(void) {
+    // src/main.c:243
+    return "Timestamp,Row,Col,x,y,z,distance,IMU_x,IMU_y,IMU_z,IMU_roll,IMU_pitch,IMU_yaw,LiDAR_x,LiDAR_y,LiDAR_z,"
+           "LiDAR_roll,LiDAR_pitch,LiDAR_yaw,EKF_x,EKF_y,EKF_z,EKF_roll,EKF_pitch,EKF_yaw\n";
+}
+
+// One frame = rows*cols lines of src/main.c:324-349 (the L5 handler, which passes a double to every
+// %.2f).  distances == NULL prints 0, imu == NULL / ekf_pos == NULL print 0.00 in their six columns: what
+// the L9 handler (main.c:437-461) means by its literal 0 arguments -- as written it hands ints to %.2f,
+// which is undefined behaviour and not reproduced.
+extern "C" size_t nav_csv_format_frame(char *buf, size_t cap, unsigned long long timestamp, int rows, int cols,
+                                       const nav_point *global_cloud, const int *distances, const double imu[6],
+                                       const nav_pos *lidar_pos, const nav_pos *ekf_pos) {
+    if (!buf || !global_cloud || !lidar_pos || rows < 1 || cols < 1) return 0;
+    // the 18 pose columns are the same text on every line of the frame
+    char tail[18 * 340 + 4];
+    const size_t tail_len = nav::csv_pose_columns(tail, imu, lidar_pos, ekf_pos);
     char *o = buf;
     char *const lim = buf + cap;
+    char head[3 * 340 + 80];
     for (int r = 0; r < rows; ++r) {
         for (int c = 0; c < cols; ++c) {
-            if ((size_t)(lim - o) < tail_len + 3 * 340 + 80) return 0;  // caller's buffer too small
             const nav_point &p = global_cloud[(size_t)r * cols + c];
-            o = fmt_uint(o, timestamp);
-            *o++ = ',';
-            o = fmt_int(o, r);
-            *o++ = ',';
-            o = fmt_int(o, c);
-            *o++ = ',';
-            o = fmt_fixed2(o, p.x);
-            *o++ = ',';
-            o = fmt_fixed2(o, p.y);
-            *o++ = ',';
-            o = fmt_fixed2(o, p.z);
-            *o++ = ',';
-            o = fmt_int(o, distances ? distances[(size_t)r * cols + c] : 0);
-            memcpy(o, tail, tail_len);
-            o += tail_len;
+            char *h = fmt_uint(head, timestamp);
+            *h++ = ',';
+            h = fmt_int(h, r);
+            *h++ = ',';
+            h = fmt_int(h, c);
+            *h++ = ',';
+            h = fmt_fixed2(h, p.x);
+            *h++ = ',';
+            h = fmt_fixed2(h, p.y);
+            *h++ = ',';
+            h = fmt_fixed2(h, p.z);
+            *h++ = ',';
+            h = fmt_int(h, distances ? distances[(size_t)r * cols + c] : 0);
+            const size_t head_len = (size_t)(h - head);
+            if ((size_t)(lim - o) < head_len + tail_len) return 0;  // caller's buffer too small
+            memcpy(o, head, head_len);
+            memcpy(o + head_len, tail, tail_len);
+            o += head_len + tail_len;
         }
     }
     return (size_t)(o - buf);

@@ -51,4 +51,19 @@ void launch_corr_stats(const nav_corr *corr, const int *corr_total, double *stat
 void launch_flatten_row(const double *row_pts, const int *row_feature, const unsigned *row_mask, double *out,
                         int *col_out, int *count, int cols, cudaStream_t stream);
 
+// ---- csvfmt.cu : CSV rows of one frame formatted on the device (src/main.c:320-352)
+struct CsvJob {
+    const double *cloud;  // [n][3] global cloud
+    const int *dist;      // [n] or null (prints 0)
+    unsigned long long ts;
+    long long n;
+    int cols, ts_len, tail_len;
+    char tail[480];  // ",%.2f" x 18 + "\n", the same on every line (formatted on the host)
+};
+size_t csv_scratch_bytes(long long n);
+// writes the text to d_text (needs n * (124 + tail_len) bytes); d_scratch[0..8) = total bytes,
+// d_scratch[8..12) = 1 if some value needs the host formatter (inf, nan, |v| >= 2^57)
+int launch_csv_format(const CsvJob &job, char *d_text, void *d_scratch, cudaStream_t stream);
+// io.cu: the 18 pose columns of a line
+
 }  // namespace nav

@@ -503,3 +503,56 @@ def test_no_device_errors_are_loud(pkg):
         pkg.Context(8, 8, device=99)
     with pytest.raises(pkg.NavError):
         pkg.Context(8, 8, device=0, n_seq=1000)
+
+
+# ------------------------------------------------------------ 8f #4: CSV rows on the GPU ----------
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(8, 8), (5, 33), (16, 1800), (64, 2048)])
+def test_csv_rows_gpu_byte_identical_to_printf(pkg, oracle, shape):
+    """nav_csv_format_frame_gpu against the oracle's snprintf restatement of src/main.c:324-349."""
+    rows, cols = shape
+    rng = np.random.default_rng(rows * 7 + cols)
+    g = rng.standard_normal((rows, cols, 3)) * 10.0 ** rng.integers(-4, 7, (rows, cols, 1))
+    k = rng.integers(0, 2 ** 20, (rows, cols, 3))
+    ties = rng.random((rows, cols, 3)) < 0.3
+    g = np.where(ties, (2 * k + 1) / 8.0 * rng.choice([-1.0, 1.0], (rows, cols, 3)), g)   # exact x.xx5 ties
+    g[0, 0] = [0.0, -0.0, 5e-324]
+    g[0, 1] = [0.005, 0.015, -0.025]
+    g[0, 2] = [2.0 ** 56, -(2.0 ** 57 - 16), 99.995]
+    d = rng.integers(-5000, 5000, (rows, cols)).astype(np.int32)
+    lp = rng.standard_normal(6) * 1000
+    ep = rng.standard_normal(6) * 1000
+    imu = rng.standard_normal(6) * 1000
+    ctx = pkg.Context(rows, cols)
+    try:
+        got = ctx.csv_rows(2 ** 33 + 5, lp, global_cloud=g, distances=d, imu=imu, ekf_pos=ep)
+        want = oracle.csv_format_frame(2 ** 33 + 5, g, lp, distances=d, imu=imu, ekf_pos=ep)
+        assert got == want
+        got = ctx.csv_rows(0, lp, global_cloud=g)
+        assert got == oracle.csv_format_frame(0, g, lp)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_csv_rows_gpu_resident_cloud_and_host_fallback(pkg, oracle, synth):
+    """global_cloud=None prints the cloud nav_slam_mapping left in HBM; inf / nan / huge values take
+    the host formatter and still give printf's bytes."""
+    rows, cols = 16, 1800
+    seq = synth.l9_sequence(2)
+    pos = np.array([10.0, -20.0, 5.0, 1.0, 2.0, 3.0])
+    ctx = pkg.Context(rows, cols)
+    try:
+        g = ctx.slam_init(pos, seq[0])
+        got = ctx.csv_rows(3, pos)
+        assert got == oracle.csv_format_frame(3, g, pos)
+        bad = g.copy()
+        bad[3, 7] = [float("inf"), float("nan"), 1e300]
+        got = ctx.csv_rows(4, pos, global_cloud=bad)
+        assert got == oracle.csv_format_frame(4, bad, pos)
+        huge_pose = pos.copy()
+        huge_pose[0] = 1e200
+        got = ctx.csv_rows(5, huge_pose, global_cloud=g)
+        assert got == oracle.csv_format_frame(5, g, huge_pose)
+    finally:
+        ctx.close()
