@@ -529,6 +529,31 @@ def run_gpu_arm(args):
               "alg_bytes_per_launch": nq * 36 // world, "achieved_gbs": nq * 36 / (q_ms * 1e-3) / 1e9}
         tree.close()
         del d_pts
+        if world == 1 and not args.big_map:
+            # config 4 the way a SLAM run produces it: 8 mapped 64x2048 frames (1 048 576 points lying on
+            # the room's surfaces) queried by the next frame's 131 072 points in image order
+            pts_a, q_a = pkg.synth.accumulated_map(8)
+            d_pa, d_qa = torch.from_numpy(pts_a).cuda(), torch.from_numpy(q_a).cuda()
+            pkg.KdTree(dev_ptr=d_pa.data_ptr(), n=pts_a.shape[0], device=local, stream=s).close()
+            spin_up()
+            e0.record(stream)
+            tree = pkg.KdTree(dev_ptr=d_pa.data_ptr(), n=pts_a.shape[0], device=local, stream=s)
+            e1.record(stream)
+            for _ in range(3):
+                tree.nn_batch_dev(d_qa.data_ptr(), nq, buf_i.data_ptr(), buf_d.data_ptr(), s)
+            e2.record(stream)
+            for _ in range(reps):
+                tree.nn_batch_dev(d_qa.data_ptr(), nq, buf_i.data_ptr(), buf_d.data_ptr(), s)
+            e3.record(stream)
+            torch.cuda.synchronize()
+            qa_ms = e2.elapsed_time(e3) / reps
+            nn["accumulated_map"] = {
+                "workload": "cfg4 as a SLAM run produces it: 8 mapped 64x2048 room frames (surfaces), queried by the "
+                            "next frame's points in image order",
+                "map_points": int(pts_a.shape[0]), "queries": nq, "build_ms": e0.elapsed_time(e1), "query_ms": qa_ms,
+                "queries_per_s": nq / (qa_ms * 1e-3), "matched": int((buf_i >= 0).sum())}
+            tree.close()
+            del d_pa, d_qa
 
     if rank == 0:
         value = world * K / (dev_ms * 1e-3)

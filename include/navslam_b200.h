@@ -86,6 +86,15 @@ int nav_transform_cloud(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos
 nav_kdtree *nav_kdtree_build(int device, const nav_point *points, size_t n);
 /* the *_dev entry points run on the given cudaStream_t (0 = legacy default stream) and do not synchronise */
 nav_kdtree *nav_kdtree_build_dev(int device, const void *dev_points, size_t n, void *cuda_stream);
+/* Split rule of the build.  CYCLIC: axis = depth % 3 as utils/kdtree.c:72 -- with distinct coordinates
+ * the exported tree is the reference's tree node for node.  WIDEST (what the two builders above use):
+ * every node splits the axis of largest extent of its points; same answers from every query (the search
+ * is exact either way), 4x faster searches on maps made of surfaces (profiles/README.md).
+ * points_on_device = 0: host points, own stream, synchronised; 1: device points on cuda_stream. */
+#define NAV_KD_SPLIT_CYCLIC 0
+#define NAV_KD_SPLIT_WIDEST 1
+nav_kdtree *nav_kdtree_build_ex(int device, const void *points, size_t n, int points_on_device,
+                                void *cuda_stream, int split_rule);
 void nav_kdtree_free(nav_kdtree *tree);
 size_t nav_kdtree_size(const nav_kdtree *tree);
 /* batched exact 1-NN.  idx[i] = -1 and dist[i] = +inf for an empty tree.  nearest_out may be NULL. */
@@ -102,8 +111,8 @@ int nav_bruteforce_nn_batch_dev(int device, const void *dev_points, size_t n, co
                                 size_t nq, void *dev_idx_out, void *dev_dist_out,
                                 int use_tensor_cores, void *cuda_stream);
 /* copy the flat node array out for inspection: nodes_out[n] points in storage (in-order) layout,
- * orig_idx_out[n] their indices in the build input */
-int nav_kdtree_export(nav_kdtree *tree, nav_point *nodes_out, int32_t *orig_idx_out);
+ * orig_idx_out[n] their indices in the build input, axis_out[n] (may be NULL) their split axes */
+int nav_kdtree_export(nav_kdtree *tree, nav_point *nodes_out, int32_t *orig_idx_out, int32_t *axis_out);
 uint64_t nav_kdtree_launch_count(const nav_kdtree *tree);
 
 /* ---- SLAM step, HOST buffers; replaces headers/slam.h:22-28 -------------------------- */

@@ -37,7 +37,7 @@ EXPORTS = [
     "nav_version", "nav_last_error", "nav_device_count", "nav_host_alloc", "nav_host_free",
     "nav_create", "nav_destroy", "nav_rows", "nav_cols", "nav_set_stream", "nav_synchronize",
     "nav_launch_count", "nav_convert_to_pointcloud", "nav_extract_feature", "nav_curvature",
-    "nav_flatten_points", "nav_transform_cloud", "nav_kdtree_build", "nav_kdtree_build_dev",
+    "nav_flatten_points", "nav_transform_cloud", "nav_kdtree_build", "nav_kdtree_build_dev", "nav_kdtree_build_ex",
     "nav_kdtree_free", "nav_kdtree_size", "nav_kdtree_nn_batch", "nav_kdtree_nn_batch_dev",
     "nav_bruteforce_nn_batch_dev", "nav_kdtree_export", "nav_kdtree_launch_count", "nav_slam_init",
     "nav_slam_match", "nav_slam_localization", "nav_slam_mapping", "nav_frontend_frame",
@@ -97,7 +97,9 @@ def load_library(build_if_missing: bool = True):
     L.nav_kdtree_nn_batch.argtypes = [vp, vp, C.c_size_t, vp, vp, vp]
     L.nav_kdtree_nn_batch_dev.argtypes = [vp, vp, C.c_size_t, vp, vp, vp]
     L.nav_bruteforce_nn_batch_dev.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp, vp, C.c_int, vp]
-    L.nav_kdtree_export.argtypes = [vp, vp, vp]
+    L.nav_kdtree_export.argtypes = [vp, vp, vp, vp]
+    L.nav_kdtree_build_ex.restype = vp
+    L.nav_kdtree_build_ex.argtypes = [C.c_int, vp, C.c_size_t, C.c_int, vp, C.c_int]
     L.nav_slam_init.argtypes = [vp, C.POINTER(NavPos), vp, vp]
     L.nav_slam_init_dev.argtypes = [vp, vp, C.POINTER(NavPos)]
     L.nav_slam_match.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), vp, C.c_size_t,
@@ -378,15 +380,24 @@ class Context:
 class KdTree:
     """nav_kdtree: flat device-resident kd-tree over n points."""
 
-    def __init__(self, points=None, device: int = 0, *, dev_ptr=None, n=None, stream=None):
+    SPLIT = {"cyclic": 0, "widest": 1}  # NAV_KD_SPLIT_* of include/navslam_b200.h
+
+    def __init__(self, points=None, device: int = 0, *, dev_ptr=None, n=None, stream=None, split=None):
+        """split: None = the library default (widest extent), "cyclic" = depth % 3 like utils/kdtree.c:72."""
         self.L = load_library()
         self.device = device
         if dev_ptr is not None:
-            self.h = self.L.nav_kdtree_build_dev(device, dev_ptr, n, stream)
+            if split is None:
+                self.h = self.L.nav_kdtree_build_dev(device, dev_ptr, n, stream)
+            else:
+                self.h = self.L.nav_kdtree_build_ex(device, dev_ptr, n, 1, stream, self.SPLIT[split])
         else:
             pts = _pts(points)
             self._n = pts.shape[0]
-            self.h = self.L.nav_kdtree_build(device, pts.ctypes.data, pts.shape[0])
+            if split is None:
+                self.h = self.L.nav_kdtree_build(device, pts.ctypes.data, pts.shape[0])
+            else:
+                self.h = self.L.nav_kdtree_build_ex(device, pts.ctypes.data, pts.shape[0], 0, None, self.SPLIT[split])
         if not self.h:
             raise NavError(self.L.nav_last_error().decode("utf-8", "replace"))
 
@@ -417,12 +428,13 @@ class KdTree:
     def nn_batch_dev(self, dev_q_ptr, nq, dev_idx_ptr, dev_dist_ptr, stream=None):
         _check(self.L.nav_kdtree_nn_batch_dev(self.h, dev_q_ptr, nq, dev_idx_ptr, dev_dist_ptr, stream), self.L)
 
-    def export(self):
+    def export(self, with_axes=False):
         n = len(self)
         nodes = np.empty((n, 3))
         idx = np.empty(n, dtype=np.int32)
-        _check(self.L.nav_kdtree_export(self.h, nodes.ctypes.data, idx.ctypes.data), self.L)
-        return nodes, idx
+        axes = np.empty(n, dtype=np.int32)
+        _check(self.L.nav_kdtree_export(self.h, nodes.ctypes.data, idx.ctypes.data, axes.ctypes.data), self.L)
+        return (nodes, idx, axes) if with_axes else (nodes, idx)
 
     def launch_count(self) -> int:
         return int(self.L.nav_kdtree_launch_count(self.h))

@@ -1119,6 +1119,8 @@ struct nav_kdtree {
     double *d_pts = nullptr;  // build input order, for nearest_out
     double *d_bbox = nullptr; // lo.xyz, hi.xyz of the points (query ordering)
     cudaStream_t stream = nullptr;
+    cudaStream_t user_stream = nullptr;  // caller's stream of the most recent *_dev call
+    bool on_user_stream = false;         // ... whose work may still be in flight
     uint64_t launches = 0;
     // query scratch
     double *d_q = nullptr, *d_dist = nullptr;
@@ -1129,15 +1131,22 @@ struct nav_kdtree {
 extern "C" void nav_kdtree_free(nav_kdtree *t) {
     if (!t) return;
     cudaSetDevice(t->device);
+    if (t->on_user_stream) cudaStreamSynchronize(t->user_stream);
     if (t->stream) cudaStreamSynchronize(t->stream);
-    for (void *p : {(void *)t->d_nodes, (void *)t->d_pts, (void *)t->d_q, (void *)t->d_dist, (void *)t->d_idx,
-                    (void *)t->d_bbox})
+    // nodes / points / box come from the stream-ordered pool (no device-wide synchronisation, no
+    // page mapping per build); the query scratch of the host path is plain cudaMalloc memory
+    for (void *p : {(void *)t->d_nodes, (void *)t->d_pts, (void *)t->d_bbox})
+        if (p) cudaFreeAsync(p, t->stream);
+    for (void *p : {(void *)t->d_q, (void *)t->d_dist, (void *)t->d_idx})
         if (p) cudaFree(p);
-    if (t->stream) cudaStreamDestroy(t->stream);
+    if (t->stream) {
+        cudaStreamSynchronize(t->stream);
+        cudaStreamDestroy(t->stream);
+    }
     delete t;
 }
 
-static nav_kdtree *kd_new(int device, size_t n) {
+static nav_kdtree *kd_new(int device, size_t n, bool on_user_stream, cudaStream_t user_stream) {
     int ndev = nav_device_count();
     if (ndev == 0) {
         fail("nav_kdtree_build: no CUDA device visible -- libnavslam_b200 has no CPU fallback");
@@ -1163,10 +1172,16 @@ static nav_kdtree *kd_new(int device, size_t n) {
     t->device = device;
     t->n = n;
     cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc((void **)&t->d_bbox, 64) != cudaSuccess ||  // 48 B box + 8 B work-queue counter
-        (n && (cudaMalloc((void **)&t->d_nodes, n * sizeof(KdNode)) != cudaSuccess ||
-               cudaMalloc((void **)&t->d_pts, n * 24) != cudaSuccess))) {
+    t->on_user_stream = on_user_stream;
+    t->user_stream = user_stream;
+    bool ok = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) == cudaSuccess;
+    const cudaStream_t as = on_user_stream ? user_stream : t->stream;  // the stream the build runs on
+    ok = ok && cudaMallocAsync((void **)&t->d_bbox, 64, as) == cudaSuccess;  // 48 B box + 8 B work-queue counter
+    if (ok && n)
+        ok = cudaMallocAsync((void **)&t->d_nodes, n * sizeof(KdNode), as) == cudaSuccess &&
+             cudaMallocAsync((void **)&t->d_pts, n * 24, as) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
         fail("nav_kdtree_build: device allocation for %zu points failed", n);
         nav_kdtree_free(t);
         return nullptr;
@@ -1174,46 +1189,51 @@ static nav_kdtree *kd_new(int device, size_t n) {
     return t;
 }
 
-extern "C" nav_kdtree *nav_kdtree_build_dev(int device, const void *dev_points, size_t n, void *cuda_stream) {
-    if (n && !dev_points) {
-        fail("nav_kdtree_build_dev: null points");
+static int default_split_rule() {
+    // NAV_KD_SPLIT=cyclic|widest overrides the rule of nav_kdtree_build / nav_kdtree_build_dev (read once)
+    static const char *e = getenv("NAV_KD_SPLIT");
+    if (e && !strcmp(e, "cyclic")) return kSplitCyclic;
+    return kSplitWidest;
+}
+
+extern "C" nav_kdtree *nav_kdtree_build_ex(int device, const void *points, size_t n, int points_on_device,
+                                           void *cuda_stream, int split_rule) {
+    const char *name = points_on_device ? "nav_kdtree_build_dev" : "nav_kdtree_build";
+    if (n && !points) {
+        fail("%s: null points", name);
         return nullptr;
     }
-    nav_kdtree *t = kd_new(device, n);
+    if (split_rule != kSplitCyclic && split_rule != kSplitWidest) {
+        fail("%s: unknown split rule %d", name, split_rule);
+        return nullptr;
+    }
+    nav_kdtree *t = kd_new(device, n, points_on_device != 0, (cudaStream_t)cuda_stream);
     if (!t) return nullptr;
-    cudaStream_t s = (cudaStream_t)cuda_stream;  // 0 = legacy default stream
+    // device input: the caller's stream (0 = legacy default stream), no synchronisation;
+    // host input: the tree's own stream, synchronised before returning
+    cudaStream_t s = points_on_device ? (cudaStream_t)cuda_stream : t->stream;
     cudaError_t e = cudaSuccess;
     if (n) {
-        e = cudaMemcpyAsync(t->d_pts, dev_points, n * 24, cudaMemcpyDeviceToDevice, s);
-        if (e == cudaSuccess) e = kd_build(t->d_pts, n, t->d_nodes, t->d_bbox, t->sm_count, s, &t->launches);
+        e = cudaMemcpyAsync(t->d_pts, points, n * 24,
+                            points_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess)
+            e = kd_build(t->d_pts, n, t->d_nodes, t->d_bbox, t->sm_count, s, &t->launches, split_rule);
+        if (e == cudaSuccess && !points_on_device) e = cudaStreamSynchronize(s);
     }
     if (e != cudaSuccess) {
-        fail("nav_kdtree_build_dev: %s", cudaGetErrorString(e));
+        fail("%s: %s", name, cudaGetErrorString(e));
         nav_kdtree_free(t);
         return nullptr;
     }
     return t;
 }
 
+extern "C" nav_kdtree *nav_kdtree_build_dev(int device, const void *dev_points, size_t n, void *cuda_stream) {
+    return nav_kdtree_build_ex(device, dev_points, n, 1, cuda_stream, default_split_rule());
+}
+
 extern "C" nav_kdtree *nav_kdtree_build(int device, const nav_point *points, size_t n) {
-    if (n && !points) {
-        fail("nav_kdtree_build: null points");
-        return nullptr;
-    }
-    nav_kdtree *t = kd_new(device, n);
-    if (!t) return nullptr;
-    cudaError_t e = cudaSuccess;
-    if (n) {
-        e = cudaMemcpyAsync(t->d_pts, points, n * 24, cudaMemcpyHostToDevice, t->stream);
-        if (e == cudaSuccess) e = kd_build(t->d_pts, n, t->d_nodes, t->d_bbox, t->sm_count, t->stream, &t->launches);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
-    }
-    if (e != cudaSuccess) {
-        fail("nav_kdtree_build: %s", cudaGetErrorString(e));
-        nav_kdtree_free(t);
-        return nullptr;
-    }
-    return t;
+    return nav_kdtree_build_ex(device, points, n, 0, nullptr, default_split_rule());
 }
 
 extern "C" size_t nav_kdtree_size(const nav_kdtree *t) { return t ? t->n : 0; }
@@ -1238,6 +1258,9 @@ extern "C" int nav_kdtree_nn_batch_dev(nav_kdtree *t, const void *dev_queries, s
     if (nq && (!dev_queries || !dev_idx || !dev_dist)) return fail("nav_kdtree_nn_batch_dev: null argument");
     CU(cudaSetDevice(t->device));
     cudaStream_t s = (cudaStream_t)cuda_stream;  // 0 = legacy default stream
+    if (t->on_user_stream && t->user_stream != s) CU(cudaStreamSynchronize(t->user_stream));  // build / last search
+    t->user_stream = s;
+    t->on_user_stream = true;
     CU(kd_nn(t->d_nodes, t->n, t->d_bbox, (const double *)dev_queries, nq, (int *)dev_idx, (double *)dev_dist,
              t->sm_count, s, &t->launches, (unsigned long long *)(t->d_bbox + 6)));
     return 0;
@@ -1249,6 +1272,10 @@ extern "C" int nav_kdtree_nn_batch(nav_kdtree *t, const nav_point *queries, size
     if (nq == 0) return 0;
     if (!queries || !idx_out || !dist_out) return fail("nav_kdtree_nn_batch: null argument");
     CU(cudaSetDevice(t->device));
+    if (t->on_user_stream) {  // a device-side build or search on the caller's stream may still be running
+        CU(cudaStreamSynchronize(t->user_stream));
+        t->on_user_stream = false;
+    }
     if (nq > t->q_cap) {
         for (void *p : {(void *)t->d_q, (void *)t->d_dist, (void *)t->d_idx})
             if (p) cudaFree(p);
@@ -1275,9 +1302,11 @@ extern "C" int nav_kdtree_nn_batch(nav_kdtree *t, const nav_point *queries, size
     return 0;
 }
 
-extern "C" int nav_kdtree_export(nav_kdtree *t, nav_point *nodes_out, int32_t *orig_idx_out) {
+extern "C" int nav_kdtree_export(nav_kdtree *t, nav_point *nodes_out, int32_t *orig_idx_out, int32_t *axis_out) {
     if (!t || !nodes_out || !orig_idx_out) return fail("nav_kdtree_export: null argument");
     CU(cudaSetDevice(t->device));
+    if (t->on_user_stream) CU(cudaStreamSynchronize(t->user_stream));
+    CU(cudaStreamSynchronize(t->stream));
     std::vector<KdNode> h(t->n);
     CU(cudaMemcpy(h.data(), t->d_nodes, t->n * sizeof(KdNode), cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < t->n; ++i) {
@@ -1285,6 +1314,7 @@ extern "C" int nav_kdtree_export(nav_kdtree *t, nav_point *nodes_out, int32_t *o
         nodes_out[i].y = h[i].y;
         nodes_out[i].z = h[i].z;
         orig_idx_out[i] = h[i].idx;
+        if (axis_out) axis_out[i] = h[i].axis;
     }
     return 0;
 }

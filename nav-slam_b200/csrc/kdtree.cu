@@ -11,11 +11,18 @@
 //
 // Build, level by level, all segments of a level at once (no recursion, no per-node allocation):
 //   1. three index lists, each sorted along one axis (radix sort of order-preserving 64-bit keys);
-//   2. at level L the list of axis L%3 already holds every segment sorted, so the median of
-//      every segment is simply its middle element: mark each point left / median / right;
-//   3. the two other lists are stably partitioned inside every segment (one prefix sum of packed
-//      left/median counts + one scatter), which keeps them sorted for the levels below.
-// After ceil(log2 n) levels the three lists coincide and are the in-order layout.
+//   2. every segment picks its split axis -- kSplitCyclic: level % 3 like the reference (the exported
+//      tree then is the reference's tree); kSplitWidest (default): the axis of largest extent, read off
+//      the two ends of the segment in each sorted list.  Maps made of surfaces (walls, floors) have
+//      axes along which a segment has no extent; cycling through them doubles the search at every such
+//      level, which the widest-extent rule avoids (4x fewer node visits on the accumulated room map);
+//   3. the list of that axis holds the segment sorted, so its median is the middle element: mark each
+//      point left / median / right;
+//   4. all three lists are stably partitioned inside every segment (one prefix sum of packed
+//      left/median counts over the 3n positions + one scatter), which keeps them sorted for the levels
+//      below (for the list of the split axis this is the identity).
+// After ceil(log2 n) levels the three lists coincide and are the in-order layout.  The split axis is
+// stored in each node, so the search does not care which rule built the tree.
 //
 // Query: one thread per query, stackless.  Child ranges are pure arithmetic on (lo,hi); the way
 // back up is recovered from two bit masks (which side was taken, parity of each ancestor's size),
@@ -68,9 +75,48 @@ __device__ __forceinline__ bool segment_of(int p, int n, int level, int &lo, int
     return true;
 }
 
+// range of segment number s (bits of s, most significant first, = sides taken from the root) at `level`
+__device__ __forceinline__ bool segment_range(int s, int n, int level, int &lo, int &hi) {
+    lo = 0;
+    hi = n;
+    for (int l = level - 1; l >= 0; --l) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if ((s >> l) & 1)
+            lo = mid + 1;
+        else
+            hi = mid;
+        if (lo >= hi) return false;
+    }
+    return true;
+}
+
+// split axis of every segment of this level, stored at the position its node will take (mid)
+__global__ void k_choose_axis(const double *__restrict__ pts, const int *__restrict__ lists, int n, int level,
+                              int rule, unsigned char *__restrict__ axis_at) {
+    const long long n_seg = 1ll << level;
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n_seg;
+         s += (long long)gridDim.x * blockDim.x) {
+        int lo, hi;
+        if (!segment_range((int)s, n, level, lo, hi)) continue;
+        int axis = level % 3;
+        if (rule == kSplitWidest) {
+            double ext[3];
+            for (int d = 0; d < 3; ++d) {
+                const double first = pts[(long long)lists[(long long)d * n + lo] * 3 + d];
+                const double last = pts[(long long)lists[(long long)d * n + hi - 1] * 3 + d];
+                ext[d] = last - first;
+            }
+            axis = 0;  // ties and NaN extents keep the lowest axis
+            if (ext[1] > ext[axis]) axis = 1;
+            if (ext[2] > ext[axis]) axis = 2;
+        }
+        axis_at[lo + ((hi - lo) >> 1)] = (unsigned char)axis;
+    }
+}
+
 // side codes: 0 left, 1 median (becomes the node), 2 right
-__global__ void k_mark(const int *__restrict__ listA, int n, int level, int *__restrict__ seg_lo,
-                       int *__restrict__ seg_mid, unsigned char *__restrict__ side) {
+__global__ void k_mark(const int *__restrict__ lists, int n, int level, const unsigned char *__restrict__ axis_at,
+                       int *__restrict__ seg_lo, int *__restrict__ seg_mid, unsigned char *__restrict__ side) {
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         int lo, hi;
         if (!segment_of(p, n, level, lo, hi)) {
@@ -81,34 +127,39 @@ __global__ void k_mark(const int *__restrict__ listA, int n, int level, int *__r
         const int mid = lo + ((hi - lo) >> 1);
         seg_lo[p] = lo;
         seg_mid[p] = mid;
-        side[listA[p]] = p < mid ? 0 : (p == mid ? 1 : 2);
+        side[lists[(long long)axis_at[mid] * n + p]] = p < mid ? 0 : (p == mid ? 1 : 2);
     }
 }
 
-__global__ void k_flags(const int *__restrict__ listX, int n, const int *__restrict__ seg_lo,
+// the three lists are handled as one array of 3n positions (list a = positions [a*n, (a+1)*n))
+__global__ void k_flags(const int *__restrict__ lists, int n, const int *__restrict__ seg_lo,
                         const unsigned char *__restrict__ side, unsigned long long *__restrict__ flags) {
+    const long long base = (long long)blockIdx.y * n;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const long long g = base + p;
         unsigned long long f = 0;
         if (seg_lo[p] >= 0) {
-            const unsigned char s = side[listX[p]];
+            const unsigned char s = side[lists[g]];
             f = s == 0 ? 1ull : (s == 1 ? (1ull << 32) : 0ull);
         }
-        flags[p] = f;
+        flags[g] = f;
     }
 }
 
-__global__ void k_scatter(const int *__restrict__ listX, int *__restrict__ listOut, int n,
+__global__ void k_scatter(const int *__restrict__ lists, int *__restrict__ lists_out, int n,
                           const int *__restrict__ seg_lo, const int *__restrict__ seg_mid,
                           const unsigned char *__restrict__ side, const unsigned long long *__restrict__ scan) {
+    const long long base = (long long)blockIdx.y * n;
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        const int idx = listX[p];
+        const long long g = base + p;
+        const int idx = lists[g];
         const int lo = seg_lo[p];
         if (lo < 0) {
-            listOut[p] = idx;
+            lists_out[g] = idx;
             continue;
         }
         const int mid = seg_mid[p];
-        const unsigned long long rel = scan[p] - scan[lo];
+        const unsigned long long rel = scan[g] - scan[base + lo];
         const int lefts = (int)(rel & 0xffffffffull), meds = (int)(rel >> 32);
         const unsigned char s = side[idx];
         int dst;
@@ -118,12 +169,12 @@ __global__ void k_scatter(const int *__restrict__ listX, int *__restrict__ listO
             dst = mid;
         else
             dst = mid + 1 + ((p - lo) - lefts - meds);
-        listOut[dst] = idx;
+        lists_out[base + dst] = idx;
     }
 }
 
 __global__ void k_emit_nodes(const double *__restrict__ pts, const int *__restrict__ order, int n,
-                             KdNode *__restrict__ nodes) {
+                             const unsigned char *__restrict__ axis_at, KdNode *__restrict__ nodes) {
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         const int i = order[p];
         KdNode nd;
@@ -131,7 +182,7 @@ __global__ void k_emit_nodes(const double *__restrict__ pts, const int *__restri
         nd.y = pts[(long long)i * 3 + 1];
         nd.z = pts[(long long)i * 3 + 2];
         nd.idx = i;
-        nd.pad = 0;
+        nd.axis = axis_at[p];
         nodes[p] = nd;
     }
 }
@@ -156,14 +207,14 @@ __global__ void k_bbox_from_lists(const double *__restrict__ pts, const int *__r
 }
 
 cudaError_t kd_build(const double *d_pts, size_t n_sz, KdNode *d_nodes, double *d_bbox, int sm_count,
-                     cudaStream_t stream, uint64_t *launches) {
+                     cudaStream_t stream, uint64_t *launches, int split_rule) {
     if (n_sz == 0) return cudaSuccess;
     if (n_sz > (size_t)0x7fffffff) return cudaErrorInvalidValue;
     const int n = (int)n_sz;
     cudaError_t status = cudaSuccess;
     unsigned long long *keys = nullptr, *keys_alt = nullptr, *flags = nullptr;
     int *idx0 = nullptr, *lists = nullptr, *lists_alt = nullptr, *seg_lo = nullptr, *seg_mid = nullptr;
-    unsigned char *side = nullptr;
+    unsigned char *side = nullptr, *axis_at = nullptr;
     void *tmp = nullptr;
     size_t tmp_sort = 0, tmp_scan = 0, tmp_bytes = 0;
     uint64_t nl = 0;
@@ -173,15 +224,17 @@ cudaError_t kd_build(const double *d_pts, size_t n_sz, KdNode *d_nodes, double *
 
     KD_CHECK(cudaMallocAsync(&keys, sizeof(unsigned long long) * n_sz * 3, stream));
     KD_CHECK(cudaMallocAsync(&keys_alt, sizeof(unsigned long long) * n_sz, stream));
-    KD_CHECK(cudaMallocAsync(&flags, sizeof(unsigned long long) * n_sz, stream));
+    KD_CHECK(cudaMallocAsync(&flags, sizeof(unsigned long long) * n_sz * 3, stream));
     KD_CHECK(cudaMallocAsync(&idx0, sizeof(int) * n_sz, stream));
     KD_CHECK(cudaMallocAsync(&lists, sizeof(int) * n_sz * 3, stream));
     KD_CHECK(cudaMallocAsync(&lists_alt, sizeof(int) * n_sz * 3, stream));
     KD_CHECK(cudaMallocAsync(&seg_lo, sizeof(int) * n_sz, stream));
     KD_CHECK(cudaMallocAsync(&seg_mid, sizeof(int) * n_sz, stream));
     KD_CHECK(cudaMallocAsync(&side, n_sz, stream));
+    KD_CHECK(cudaMallocAsync(&axis_at, n_sz, stream));
+    KD_CHECK(cudaMemsetAsync(axis_at, 0, n_sz, stream));
     KD_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys, keys_alt, idx0, lists, n, 0, 64, stream));
-    KD_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, flags, flags, n, stream));
+    KD_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, flags, flags, 3ll * n, stream));
     tmp_bytes = tmp_sort > tmp_scan ? tmp_sort : tmp_scan;
     KD_CHECK(cudaMallocAsync(&tmp, tmp_bytes, stream));
 
@@ -198,27 +251,21 @@ cudaError_t kd_build(const double *d_pts, size_t n_sz, KdNode *d_nodes, double *
     }
     {
         int *cur = lists, *alt = lists_alt;
+        const dim3 grid3((unsigned)grid, 3u);  // blockIdx.y = list
         for (int level = 0; (n >> level) >= 2; ++level) {
-            const int a = level % 3, b = (a + 1) % 3, c = (a + 2) % 3;
-            k_mark<<<grid, threads, 0, stream>>>(cur + a * n_sz, n, level, seg_lo, seg_mid, side);
-            ++nl;
-            const int others[2] = {b, c};
-            for (int t = 0; t < 2; ++t) {
-                const int *src = cur + others[t] * n_sz;
-                int *dst = alt + others[t] * n_sz;
-                k_flags<<<grid, threads, 0, stream>>>(src, n, seg_lo, side, flags);
-                KD_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_scan, flags, flags, n, stream));
-                k_scatter<<<grid, threads, 0, stream>>>(src, dst, n, seg_lo, seg_mid, side, flags);
-                nl += 4;
-            }
-            // list a is already partitioned (it is sorted along the split axis): carry it over
-            KD_CHECK(cudaMemcpyAsync(alt + a * n_sz, cur + a * n_sz, sizeof(int) * n_sz,
-                                     cudaMemcpyDeviceToDevice, stream));
+            long long sgrid = ((1ll << level) + threads - 1) / threads;
+            if (sgrid > grid) sgrid = grid;
+            k_choose_axis<<<(int)sgrid, threads, 0, stream>>>(d_pts, cur, n, level, split_rule, axis_at);
+            k_mark<<<grid, threads, 0, stream>>>(cur, n, level, axis_at, seg_lo, seg_mid, side);
+            k_flags<<<grid3, threads, 0, stream>>>(cur, n, seg_lo, side, flags);
+            KD_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_scan, flags, flags, 3ll * n, stream));
+            k_scatter<<<grid3, threads, 0, stream>>>(cur, alt, n, seg_lo, seg_mid, side, flags);
+            nl += 6;
             int *t2 = cur;
             cur = alt;
             alt = t2;
         }
-        k_emit_nodes<<<grid, threads, 0, stream>>>(d_pts, cur, n, d_nodes);
+        k_emit_nodes<<<grid, threads, 0, stream>>>(d_pts, cur, n, axis_at, d_nodes);
         ++nl;
     }
     KD_CHECK(cudaGetLastError());
@@ -232,6 +279,7 @@ done:
     cudaFreeAsync(seg_lo, stream);
     cudaFreeAsync(seg_mid, stream);
     cudaFreeAsync(side, stream);
+    cudaFreeAsync(axis_at, stream);
     cudaFreeAsync(tmp, stream);
     if (launches) *launches += nl;
     return status;
@@ -239,14 +287,16 @@ done:
 
 // ------------------------------------------------------------------------------ query ------
 __device__ __forceinline__ void load_node(const KdNode *__restrict__ nodes, int i, double &x, double &y,
-                                          double &z, int &idx) {
+                                          double &z, int &idx, int &axis) {
     const double2 *p = reinterpret_cast<const double2 *>(nodes + i);
     const double2 a = __ldg(p);
     const double2 b = __ldg(p + 1);
     x = a.x;
     y = a.y;
     z = b.x;
-    idx = (int)(__double_as_longlong(b.y) & 0xffffffffll);
+    const long long w = __double_as_longlong(b.y);
+    idx = (int)(w & 0xffffffffll);
+    axis = (int)(w >> 32);
 }
 
 __device__ __forceinline__ double node_axis(const KdNode *__restrict__ nodes, int i, int axis) {
@@ -297,16 +347,17 @@ k_kd_nn(const KdNode *__restrict__ nodes, int n, const double *__restrict__ quer
 
     int lo = 0, hi = n, depth = 0;
     unsigned path = 0, par = 0;  // bit d: side taken below the depth-d ancestor (1 = right) / its size parity
+    unsigned long long axes = 0;  // two bits per depth: split axis of the ancestor at that depth
     bool arriving_down = true;
     while (true) {
         const int mid = lo + ((hi - lo) >> 1);
-        const int axis = depth % 3;
         bool go_far = false;
         double diff;
         if (arriving_down) {
             double x, y, z;
-            int idx;
-            load_node(nodes, mid, x, y, z, idx);
+            int idx, axis;
+            load_node(nodes, mid, x, y, z, idx, axis);
+            axes = (axes & ~(3ull << (2 * depth))) | ((unsigned long long)axis << (2 * depth));
             // operand order root - target (utils/kdtree.c:16); squared, so the sign is immaterial
             const double d = dsq3(dsub(x, qx), dsub(y, qy), dsub(z, qz));
             if (d < best || (d == best && idx < bidx)) {
@@ -329,6 +380,7 @@ k_kd_nn(const KdNode *__restrict__ nodes, int n, const double *__restrict__ quer
             go_far = true;
             path = (path & ~(1u << depth)) | ((unsigned)near_right << depth);
         } else {
+            const int axis = (int)((axes >> (2 * depth)) & 3ull);
             const double key = node_axis(nodes, mid, axis);
             diff = dsub(axis == 0 ? qx : (axis == 1 ? qy : qz), key);
             const bool near_right = !(diff < 0.0);
@@ -415,11 +467,10 @@ k_kd_nn_conv(const KdNode *__restrict__ nodes, int n, const double *__restrict__
         if (done) continue;
         // ---- one node step
         const int mid = lo + ((hi - lo) >> 1);
-        const int axis = depth - 3 * ((depth * 11) >> 5);  // depth % 3 for depth < 32
         const unsigned bit = 1u << depth;
         double x, y, z;
-        int idx;
-        load_node(nodes, mid, x, y, z, idx);
+        int idx, axis;
+        load_node(nodes, mid, x, y, z, idx, axis);
         const double diff = dsub(axis == 0 ? qx : (axis == 1 ? qy : qz), axis == 0 ? x : (axis == 1 ? y : z));
         const double plane = dmul(diff, diff);
         if (fresh) {
@@ -481,6 +532,9 @@ k_kd_nn_conv(const KdNode *__restrict__ nodes, int n, const double *__restrict__
 // pushed with their plane distance on the way down and popped (or discarded) later, so no ancestor
 // is ever re-read and nothing climbs level by level.  Visits exactly the nodes the stackless kernel
 // visits (same pruning rule, same lexicographic compare) -> identical answers.
+// (Tried on top of this: the incremental per-axis cell bound of Arya & Mount, offsets stacked as
+// floats rounded toward zero.  Exact, but 10-15 % slower on every map measured -- the plane test
+// already rejects nearly everything the stronger bound would; profiles/README.md.)
 __global__ void __launch_bounds__(128)
 k_kd_nn_stack(const KdNode *__restrict__ nodes, int n, const double *__restrict__ queries, long long nq,
               const int *__restrict__ perm, int *__restrict__ idx_out, double *__restrict__ dist_out) {
@@ -495,29 +549,27 @@ k_kd_nn_stack(const KdNode *__restrict__ nodes, int n, const double *__restrict_
     const double qx = queries[qi * 3], qy = queries[qi * 3 + 1], qz = queries[qi * 3 + 2];
     double best = INFINITY;
     int bidx = -1;
-    int st_lo[32], st_hi[32], st_d[32];
+    int st_lo[32], st_hi[32];
     double st_plane[32];
     int sp = 0;
-    int lo = 0, hi = n, depth = 0;
+    int lo = 0, hi = n;
     while (true) {
         while (lo < hi) {
             const int mid = lo + ((hi - lo) >> 1);
             double x, y, z;
-            int idx;
-            load_node(nodes, mid, x, y, z, idx);
+            int idx, axis;
+            load_node(nodes, mid, x, y, z, idx, axis);
             const double d = dsq3(dsub(x, qx), dsub(y, qy), dsub(z, qz));
             if (d < best || (d == best && idx < bidx)) {
                 best = d;
                 bidx = idx;
             }
-            const int axis = depth % 3;
             const double diff = dsub(axis == 0 ? qx : (axis == 1 ? qy : qz), axis == 0 ? x : (axis == 1 ? y : z));
             const bool near_right = !(diff < 0.0);
             const int flo = near_right ? lo : mid + 1, fhi = near_right ? mid : hi;
             if (flo < fhi) {
                 st_lo[sp] = flo;
                 st_hi[sp] = fhi;
-                st_d[sp] = depth + 1;
                 st_plane[sp] = dmul(diff, diff);
                 ++sp;
             }
@@ -525,7 +577,6 @@ k_kd_nn_stack(const KdNode *__restrict__ nodes, int n, const double *__restrict_
                 lo = mid + 1;
             else
                 hi = mid;
-            ++depth;
         }
         // next pending far subtree whose plane is still within reach (NaN planes are never pruned)
         bool found = false;
@@ -534,7 +585,6 @@ k_kd_nn_stack(const KdNode *__restrict__ nodes, int n, const double *__restrict_
             if (!(st_plane[sp] > best)) {
                 lo = st_lo[sp];
                 hi = st_hi[sp];
-                depth = st_d[sp];
                 found = true;
                 break;
             }
@@ -556,13 +606,14 @@ cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const d
     // cost ~75 us, so it is off unless NAV_KD_SORT=1 (e.g. for much larger query sets).
     static const int sort_mode = getenv("NAV_KD_SORT") ? atoi(getenv("NAV_KD_SORT")) : 0;
     const bool sort_queries = sort_mode && d_bbox && n >= 4096 && nq >= 8192 && nq < (size_t)0x7fffffff;
-    // Kernel choice by measurement on B200 (131 072 queries; profiles/README.md): the plain stackless
-    // kernel wins up to ~1 M points (127 vs 137 us), the converged work-refilling kernel wins on
-    // maps that no longer fit in L2 (10 M points: 199 vs 219 us); a short explicit stack is faster only
-    // around 64 K points and slower at 10 M, so it stays opt-in.  NAV_KD_KERNEL = plain|conv|stack overrides.
+    // Kernel choice by measurement on B200 (131 072 queries, widest-extent trees; profiles/README.md):
+    // the short explicit stack wins up to ~1 M points and on surface-like maps (accumulated room map,
+    // 1 M points: 153 us against 164 plain / 178 converged), the plain stackless kernel around 4 M uniform
+    // points (126 vs 151 us), the converged work-refilling kernel on maps that no longer fit in L2
+    // (10 M points: 164 vs 180 plain vs 205 stack).  NAV_KD_KERNEL = plain|conv|stack overrides.
     static const char *kk = getenv("NAV_KD_KERNEL");  // read once
-    const int use_stack = kk && !strcmp(kk, "stack");
-    const bool use_conv = kk ? !strcmp(kk, "conv") : n >= ((size_t)1 << 22);
+    const bool use_stack = kk ? !strcmp(kk, "stack") : n < ((size_t)1 << 21);
+    const bool use_conv = kk ? !strcmp(kk, "conv") : n >= ((size_t)1 << 23);
     if (!sort_queries && use_conv && d_counter && n > 0) {
         cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
         unsigned pgrid = (unsigned)sm_count * 12u;  // 12 x 128 threads = 48 warps per SM (40 registers)

@@ -150,6 +150,16 @@ def map_points(n: int, *, variant: str = "uniform", seed: int = 4000) -> np.ndar
     raise ValueError(variant)
 
 
+def accumulated_map(n_frames: int = 8, rows: int = 64, cols: int = 2048, *, start: int = 0):
+    """BASELINE config 4 as a SLAM run produces it: the global clouds of n_frames consecutive frames
+    (each moved by its true pose) concatenated in mapping order -- 8 x 64 x 2048 = 1 048 576 points --
+    and the next frame, moved by its predicted pose, as the 131 072 queries in image order."""
+    frames = room_sequence(rows, cols, n_frames + 1, start=start)
+    parts = [frames[f].reshape(-1, 3) + true_pose(start + f)[:3] for f in range(n_frames)]
+    queries = frames[n_frames].reshape(-1, 3) + true_pose(start + n_frames)[:3]
+    return np.ascontiguousarray(np.concatenate(parts)), np.ascontiguousarray(queries)
+
+
 def map_queries(points: np.ndarray, nq: int, *, variant: str = "jitter", seed: int = 4001) -> np.ndarray:
     rng = np.random.default_rng(seed)
     if variant == "jitter":

@@ -350,24 +350,31 @@ def test_localization_from_sufficient_statistics(ctxs, oracle, synth):
 
 
 # ------------------------------------------------------------------ kd-tree (a5 / a6) --------
-def _check_inorder(nodes, lo, hi, depth, bounds):
-    """Recursive invariant check of the in-order layout: left keys <= node key <= right keys."""
+def _check_inorder(nodes, axes, lo, hi, depth, split):
+    """Recursive invariant check of the in-order layout: left keys <= node key <= right keys along the
+    node's split axis; cyclic trees split depth % 3, widest-extent trees the axis of largest extent."""
     stack = [(lo, hi, depth)]
     while stack:
         lo, hi, d = stack.pop()
         if hi - lo <= 1:
             continue
         mid = lo + (hi - lo) // 2
-        a = d % 3
+        a = int(axes[mid])
+        if split == "cyclic":
+            assert a == d % 3
+        else:
+            ext = nodes[lo:hi].max(axis=0) - nodes[lo:hi].min(axis=0)
+            assert ext[a] == ext.max() and a == int(np.argmax(ext))
         k = nodes[mid, a]
         assert (nodes[lo:mid, a] <= k).all() and (nodes[mid + 1:hi, a] >= k).all()
         stack.append((lo, mid, d + 1))
         stack.append((mid + 1, hi, d + 1))
 
 
-@pytest.mark.parametrize("kind", ["uniform", "clustered", "integer", "duplicates", "sorted", "all_equal"])
+@pytest.mark.parametrize("split", ["widest", "cyclic"])
+@pytest.mark.parametrize("kind", ["uniform", "clustered", "integer", "duplicates", "sorted", "all_equal", "planes"])
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 1000, 30000])
-def test_kdtree_exact_lowest_index(pkg, oracle, synth, kind, n):
+def test_kdtree_exact_lowest_index(pkg, oracle, synth, kind, n, split):
     rng = np.random.default_rng(n + 13)
     if kind == "uniform":
         pts = synth.map_points(n, seed=n)
@@ -379,15 +386,19 @@ def test_kdtree_exact_lowest_index(pkg, oracle, synth, kind, n):
         pts = np.repeat(rng.normal(0, 100, size=((n + 3) // 4, 3)), 4, axis=0)[:n]
     elif kind == "sorted":
         pts = np.stack([np.arange(n, dtype=np.float64)] * 3, axis=1)
+    elif kind == "planes":  # walls: one coordinate constant per point, the case cyclic splitting handles badly
+        pts = rng.uniform(-4000, 4000, size=(n, 3))
+        if n:
+            pts[np.arange(n), rng.integers(0, 3, n)] = rng.choice([-4000.0, 4000.0], n)
     else:
         pts = np.full((n, 3), 3.25)
-    tree = pkg.KdTree(pts, device=0)
+    tree = pkg.KdTree(pts, device=0, split=split)
     assert len(tree) == n
-    nodes, oidx = tree.export()
+    nodes, oidx, axes = tree.export(with_axes=True)
     if n:
         assert np.array_equal(np.sort(oidx), np.arange(n))
         assert np.array_equal(nodes, pts[oidx])
-        _check_inorder(nodes, 0, n, 0, None)
+        _check_inorder(nodes, axes, 0, n, 0, split)
     nq = 500
     q = (pts[rng.integers(0, n, size=nq)] + rng.normal(0, 3, size=(nq, 3))) if n else rng.normal(size=(nq, 3))
     if kind in ("integer", "all_equal"):
@@ -407,10 +418,19 @@ def test_kdtree_same_tree_as_reference_when_keys_distinct(pkg, oracle, synth):
     pts = synth.map_points(5000, seed=77)
     h, perm = oracle.tree_build(pts)
     oracle.tree_free(h)
-    tree = pkg.KdTree(pts, device=0)
+    tree = pkg.KdTree(pts, device=0, split="cyclic")
     nodes, _ = tree.export()
     assert np.array_equal(nodes, perm)
     tree.close()
+    # the default (widest-extent) tree is a different tree with the same answers
+    wide = pkg.KdTree(pts, device=0)
+    q = synth.map_queries(pts, 2000, seed=78)
+    assert not np.array_equal(wide.export()[0], perm)
+    cyc = pkg.KdTree(pts, device=0, split="cyclic")
+    a, b = wide.nn_batch(q), cyc.nn_batch(q)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    wide.close()
+    cyc.close()
 
 
 def test_kdtree_special_values(pkg, oracle):
