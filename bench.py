@@ -134,6 +134,7 @@ def _ref_frames_worker(args):
     if use_ref:
         ref = RefLib(ROWS, COLS)
         t_total = 0.0
+        ph = {"a3_extract_feature": 0.0, "a7_transform": 0.0, "a6_nn_search": 0.0, "a4_a5_flatten_build": 0.0}
         feat_prev = ref.extract_feature(frames[0])
         g_prev = o.transform(frames[0], poses_for(start)[2])
         trees, _, _ = ref.build_rows(g_prev, feat_prev)
@@ -150,9 +151,13 @@ def _ref_frames_worker(args):
             ref.free_rows(trees)
             trees, _, t_build = ref.build_rows(g, feat)                             # a4 + a5
             t_total += t_feat + (t2 - t1) + t_nn + t_build
+            ph["a3_extract_feature"] += t_feat
+            ph["a7_transform"] += t2 - t1
+            ph["a6_nn_search"] += t_nn
+            ph["a4_a5_flatten_build"] += t_build
             del t0
         ref.free_rows(trees)
-        return t_total, count, "reference"
+        return t_total, count, "reference", {k: 1e3 * v / count for k, v in ph.items()}
     slam = o.slam(ROWS, COLS, 0)
     slam.init(poses_for(start)[2], frames[0])
     t0 = time.perf_counter()
@@ -161,7 +166,7 @@ def _ref_frames_worker(args):
         slam.frontend_frame(frames[i], pred, last, final)
     dt = time.perf_counter() - t0
     slam.close()
-    return dt, count, "port"
+    return dt, count, "port", None
 
 
 def cpu_baseline_single_core(n_frames: int):
@@ -172,13 +177,13 @@ def cpu_baseline_single_core(n_frames: int):
         pinned = False
     import multiprocessing as mp
     with mp.get_context("fork").Pool(1) as pool:
-        dt, cnt, kind = pool.map(_ref_frames_worker, [(0, 0, n_frames)])[0]
+        dt, cnt, kind, phases = pool.map(_ref_frames_worker, [(0, 0, n_frames)])[0]
     if pinned:
         os.sched_setaffinity(0, set(range(os.cpu_count() or 1)))
     return {"value": cnt / dt, "unit": "frames/s", "cores": 1, "kind": kind,
             "sample": f"{cnt} frames of the 64x2048 sequence; extract_feature + per-row flattenPoints/"
                       f"buildKDTree + nearestNeighborSearch per labelled point, one core",
-            "ms_per_frame": 1e3 * dt / cnt}
+            "ms_per_frame": 1e3 * dt / cnt, "phase_ms_per_frame": phases}
 
 
 def run_reference_arm(args):

@@ -24,11 +24,14 @@
 // After ceil(log2 n) levels the three lists coincide and are the in-order layout.  The split axis is
 // stored in each node, so the search does not care which rule built the tree.
 //
-// Query: one thread per query, stackless.  Child ranges are pure arithmetic on (lo,hi); the way
-// back up is recovered from two bit masks (which side was taken, parity of each ancestor's size),
-// so the traversal keeps no stack and re-reads only the split coordinate of an ancestor (L1/L2
-// hits).  Far subtrees are visited iff the rounded plane distance^2 is <= the current best dsq;
-// candidates compare lexicographically on (dsq, original index): exact NN, lowest index on ties.
+// Query: one thread per query.  Child ranges are pure arithmetic on (lo,hi).  Three interchangeable
+// kernels (identical answers, chosen by measurement in kd_nn()): k_kd_nn_stack keeps pending far
+// subtrees on a 32-entry thread-local stack (the default); k_kd_nn / k_kd_nn_conv are stackless -- the
+// way back up is recovered from two bit masks (which side was taken, parity of each ancestor's size)
+// and only the split coordinate of an ancestor is re-read (L1/L2 hits).  Subtrees of <= 8 nodes are
+// scanned as a contiguous run.  Far subtrees are visited iff the rounded plane distance^2 is <= the
+// current best dsq; candidates compare lexicographically on (dsq, original index): exact NN, lowest
+// index on ties.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -303,6 +306,25 @@ __device__ __forceinline__ double node_axis(const KdNode *__restrict__ nodes, in
     return __ldg(reinterpret_cast<const double *>(nodes + i) + axis);
 }
 
+// Subtrees of at most kKdBucket nodes are a contiguous run of the in-order array: all three search
+// kernels evaluate such a run point by point (independent loads, converged lanes) instead of walking it.
+// Measured on B200 with the short-stack kernel, 131 072 queries: bucket 1 / 4 / 8 / 16 -> 107 / 98 / 88 / 98 us
+// on 1 M uniform points, 169 / 148 / 138 / 162 us on the accumulated room map.
+constexpr int kKdBucket = 8;
+__device__ __forceinline__ void scan_run(const KdNode *__restrict__ nodes, int lo, int hi, double qx, double qy,
+                                         double qz, double &best, int &bidx) {
+    for (int i = lo; i < hi; ++i) {
+        double x, y, z;
+        int idx, axis;
+        load_node(nodes, i, x, y, z, idx, axis);
+        const double d = dsq3(dsub(x, qx), dsub(y, qy), dsub(z, qz));
+        if (d < best || (d == best && idx < bidx)) {
+            best = d;
+            bidx = idx;
+        }
+    }
+}
+
 // Morton (Z-order) keys of the queries, 10 bits per axis inside the tree's bounding box: sorting
 // the queries by this key makes the 32 lanes of a warp walk nearly the same root-to-leaf paths
 // (coherent branches, shared cache lines).  Ordering only affects speed, never the answers.
@@ -353,7 +375,9 @@ k_kd_nn(const KdNode *__restrict__ nodes, int n, const double *__restrict__ quer
         const int mid = lo + ((hi - lo) >> 1);
         bool go_far = false;
         double diff;
-        if (arriving_down) {
+        if (arriving_down && hi - lo <= kKdBucket) {
+            scan_run(nodes, lo, hi, qx, qy, qz, best, bidx);  // then climb
+        } else if (arriving_down) {
             double x, y, z;
             int idx, axis;
             load_node(nodes, mid, x, y, z, idx, axis);
@@ -465,47 +489,52 @@ k_kd_nn_conv(const KdNode *__restrict__ nodes, int n, const double *__restrict__
         }
         if (__all_sync(0xffffffffu, done)) break;
         if (done) continue;
-        // ---- one node step
+        // ---- one node step (or one small contiguous subtree evaluated point by point)
         const int mid = lo + ((hi - lo) >> 1);
         const unsigned bit = 1u << depth;
-        double x, y, z;
-        int idx, axis;
-        load_node(nodes, mid, x, y, z, idx, axis);
-        const double diff = dsub(axis == 0 ? qx : (axis == 1 ? qy : qz), axis == 0 ? x : (axis == 1 ? y : z));
-        const double plane = dmul(diff, diff);
-        if (fresh) {
-            // operand order root - target (utils/kdtree.c:16); squared, so the sign is immaterial
-            const double d = dsq3(dsub(x, qx), dsub(y, qy), dsub(z, qz));
-            if (d < best || (d == best && idx < bidx)) {
-                best = d;
-                bidx = idx;
+        if (fresh && hi - lo <= kKdBucket) {
+            scan_run(nodes, lo, hi, qx, qy, qz, best, bidx);
+            fresh = false;
+        } else {
+            double x, y, z;
+            int idx, axis;
+            load_node(nodes, mid, x, y, z, idx, axis);
+            const double diff = dsub(axis == 0 ? qx : (axis == 1 ? qy : qz), axis == 0 ? x : (axis == 1 ? y : z));
+            const double plane = dmul(diff, diff);
+            if (fresh) {
+                // operand order root - target (utils/kdtree.c:16); squared, so the sign is immaterial
+                const double d = dsq3(dsub(x, qx), dsub(y, qy), dsub(z, qz));
+                if (d < best || (d == best && idx < bidx)) {
+                    best = d;
+                    bidx = idx;
+                }
+                const bool near_right = !(diff < 0.0);  // target < node -> left, else right (kdtree.c:130-141)
+                par = (par & ~bit) | ((unsigned)((hi - lo) & 1) << depth);
+                path = (path & ~bit) | ((unsigned)near_right << depth);
+                const bool far_nonempty = near_right ? (lo < mid) : (mid + 1 < hi);
+                // '<=' on squares keeps exact ties reachable (lowest index wins); NaN planes are never pruned
+                pend = (far_nonempty && !(plane > best)) ? (pend | bit) : (pend & ~bit);
+                const int clo = near_right ? mid + 1 : lo, chi = near_right ? hi : mid;
+                if (clo < chi) {
+                    lo = clo;
+                    hi = chi;
+                    ++depth;
+                    continue;
+                }
+                fresh = false;  // empty near side: handle this node as a return visit right away
             }
-            const bool near_right = !(diff < 0.0);  // target < node -> left, else right (kdtree.c:130-141)
-            par = (par & ~bit) | ((unsigned)((hi - lo) & 1) << depth);
-            path = (path & ~bit) | ((unsigned)near_right << depth);
-            const bool far_nonempty = near_right ? (lo < mid) : (mid + 1 < hi);
-            // '<=' on squares keeps exact ties reachable (lowest index wins); NaN planes are never pruned
-            pend = (far_nonempty && !(plane > best)) ? (pend | bit) : (pend & ~bit);
-            const int clo = near_right ? mid + 1 : lo, chi = near_right ? hi : mid;
-            if (clo < chi) {
-                lo = clo;
-                hi = chi;
+            if ((pend & bit) && !(plane > best)) {  // far side still within reach: go there
+                const bool near_right = (path >> depth) & 1u;
+                pend &= ~bit;
+                path ^= bit;
+                if (near_right)
+                    hi = mid;
+                else
+                    lo = mid + 1;
                 ++depth;
+                fresh = true;
                 continue;
             }
-            fresh = false;  // empty near side: handle this node as a return visit right away
-        }
-        if ((pend & bit) && !(plane > best)) {  // far side still within reach: go there
-            const bool near_right = (path >> depth) & 1u;
-            pend &= ~bit;
-            path ^= bit;
-            if (near_right)
-                hi = mid;
-            else
-                lo = mid + 1;
-            ++depth;
-            fresh = true;
-            continue;
         }
         pend &= ~bit;
         const unsigned below = pend & (bit - 1u);
@@ -555,6 +584,10 @@ k_kd_nn_stack(const KdNode *__restrict__ nodes, int n, const double *__restrict_
     int lo = 0, hi = n;
     while (true) {
         while (lo < hi) {
+            if (hi - lo <= kKdBucket) {
+                scan_run(nodes, lo, hi, qx, qy, qz, best, bidx);
+                break;
+            }
             const int mid = lo + ((hi - lo) >> 1);
             double x, y, z;
             int idx, axis;
@@ -606,14 +639,15 @@ cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const d
     // cost ~75 us, so it is off unless NAV_KD_SORT=1 (e.g. for much larger query sets).
     static const int sort_mode = getenv("NAV_KD_SORT") ? atoi(getenv("NAV_KD_SORT")) : 0;
     const bool sort_queries = sort_mode && d_bbox && n >= 4096 && nq >= 8192 && nq < (size_t)0x7fffffff;
-    // Kernel choice by measurement on B200 (131 072 queries, widest-extent trees; profiles/README.md):
-    // the short explicit stack wins up to ~1 M points and on surface-like maps (accumulated room map,
-    // 1 M points: 153 us against 164 plain / 178 converged), the plain stackless kernel around 4 M uniform
-    // points (126 vs 151 us), the converged work-refilling kernel on maps that no longer fit in L2
-    // (10 M points: 164 vs 180 plain vs 205 stack).  NAV_KD_KERNEL = plain|conv|stack overrides.
+    // Kernel choice by measurement on B200 (131 072 queries, widest-extent trees, 8-node runs scanned;
+    // profiles/README.md), short stack / plain stackless / converged stackless:
+    //   1 M uniform points 80 / 96 / 108 us, 4 M 124 / 126 / 144 us, 10 M 164 / 178 / 171 us,
+    //   accumulated room map (1 M points on surfaces) 122 / 162 / 185 us.
+    // The short stack wins or ties everywhere, so it is the default; NAV_KD_KERNEL = plain|conv|stack
+    // selects the others (same answers).
     static const char *kk = getenv("NAV_KD_KERNEL");  // read once
-    const bool use_stack = kk ? !strcmp(kk, "stack") : n < ((size_t)1 << 21);
-    const bool use_conv = kk ? !strcmp(kk, "conv") : n >= ((size_t)1 << 23);
+    const bool use_stack = kk ? !strcmp(kk, "stack") : true;
+    const bool use_conv = kk && !strcmp(kk, "conv");
     if (!sort_queries && use_conv && d_counter && n > 0) {
         cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
         unsigned pgrid = (unsigned)sm_count * 12u;  // 12 x 128 threads = 48 warps per SM (40 registers)
