@@ -500,13 +500,14 @@ static PoseBatch pose_batch(const nav_ctx *c, const nav_pos *pos, const nav_pos 
 // the whole front-end frame in ONE launch: labels (a3) + queries (a7) + exact per-row NN against the
 // current map (a6) + the next map from the final pose (a7, a4/a5) into the other map buffer
 static void run_frame_fused(nav_ctx *c, const double *d_cloud, int *d_labels, int *d_nn_idx, double *d_nn_dist,
-                            const nav_pos *pos_predict, const nav_pos *pos_last, const nav_pos *pos_final) {
+                            const nav_pos *pos_predict, const nav_pos *pos_last, const nav_pos *pos_final,
+                            bool pdl = false) {
     MatchOut out = {d_nn_idx, d_nn_dist, c->d_corr_rows, c->d_corr_row_count};
     const PoseBatch loc = pose_batch(c, pos_predict, pos_last), fin = pose_batch(c, pos_final, nullptr);
     {
         ProfScope ps(c, &c->prof_match);
         launch_frame_match(d_cloud, d_labels, true, c->map, out, loc, c->n_seq, c->rows, c->cols, c->d_n_exact,
-                           c->stream, &c->map_alt, &fin);
+                           c->stream, &c->map_alt, &fin, pdl && !c->prof);
     }
     c->launches++;
     std::swap(c->map, c->map_alt);
@@ -1062,7 +1063,10 @@ extern "C" int nav_frontend_sequence_dev(nav_ctx *c, const void *dev_frames, siz
     for (size_t f = 0; f < n_frames; ++f) {
         const double *cl = base + f * c->ntot * 3;
         const size_t o = f * (size_t)c->n_seq;
-        run_frame_fused(c, cl, c->d_labels, c->d_nn_idx, c->d_nn_dist, pos_predict + o, pos_last + o, pos_final + o);
+        // consecutive launches overlap (programmatic dependent launch): frame f+1 computes its labels
+        // while frame f finishes its searches
+        run_frame_fused(c, cl, c->d_labels, c->d_nn_idx, c->d_nn_dist, pos_predict + o, pos_last + o, pos_final + o,
+                        /*pdl=*/true);
     }
     c->cloud_resident = false;
     CU(cudaGetLastError());

@@ -41,7 +41,7 @@ void launch_frame_map(const double *cloud, const int *labels, const RowMap &map,
 void launch_frame_match(const double *cloud, int *labels, bool fused_labels, const RowMap &map,
                         const MatchOut &out, const PoseBatch &poses, int n_seq, int rows, int cols,
                         unsigned *n_exact, cudaStream_t stream, const RowMap *map_next = nullptr,
-                        const PoseBatch *final_poses = nullptr);
+                        const PoseBatch *final_poses = nullptr, bool pdl = false);
 void launch_dedupe(const double *cloud, const int *labels, const RowMap &map, const MatchOut &out,
                    const PoseBatch &poses, int n_seq, int rows, int cols, cudaStream_t stream);
 void launch_gather_corr(const nav_corr *corr_rows, const int *corr_row_count, nav_corr *corr_out,

@@ -233,7 +233,8 @@ template <bool kFusedLabels, bool kFuseMap>
 __global__ void __launch_bounds__(kTile, NAV_MATCH_MIN_CTAS)
 k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap map, MatchOut out,
               const __grid_constant__ PoseBatch poses, int rows, int cols, int tiles_per_row,
-              unsigned *__restrict__ n_exact, RowMap map_next, const __grid_constant__ PoseBatch final_poses) {
+              unsigned *__restrict__ n_exact, RowMap map_next, const __grid_constant__ PoseBatch final_poses,
+              int pdl) {
     __shared__ StencilSmem s;
     const int rid = blockIdx.x / tiles_per_row;
     const int tile = blockIdx.x % tiles_per_row;
@@ -251,7 +252,8 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
     const float4 *m_sbox = map.sbox + (long long)rid * map.n_super * 2;
     const int n_leaf = map.n_chunks, n_sup = map.n_super;
     const int leaf0 = tile * kChunksPerSuper - 1;  // first leaf of the prefetched neighbourhood (may be -1)
-    {   // asynchronous prefetch (cp.async) of the neighbourhood; consumed after the label phase
+    // asynchronous prefetch (cp.async) of the neighbourhood; consumed after the compaction
+    auto prefetch_map = [&]() {
         const int col_lo = leaf0 * kChunk;
         for (int i = threadIdx.x; i < kNbLeaves * kChunk * 3; i += kTile) {
             const int col = col_lo + i / 3;
@@ -266,12 +268,24 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
         } else if (threadIdx.x >= 128 && (int)threadIdx.x < 128 + 2 * min(n_sup, kMaxSuperSmem)) {
             cp_async16(&sm.sbox[threadIdx.x - 128], m_sbox + (threadIdx.x - 128));
         }
-    }
-    int label;
+    };
+    // Programmatic dependent launch (pdl != 0, kernel launched with the stream-serialisation attribute):
+    // the next frame's launch may start while this one still runs.  Everything in front of
+    // griddepcontrol.wait touches only this frame's own cloud (and shared memory); the previous frame's
+    // map and every global store come after it, when the previous grid has completed and flushed.
+    if (pdl) asm volatile("griddepcontrol.launch_dependents;");
+    if (!pdl) prefetch_map();
+    int label = 0;
     if (kFusedLabels) {
         tile_stage(s, cloud + base * 3, c0, cols);
         __syncthreads();
         label = tile_labels_filtered(s, c0, cols, n_exact);
+    }
+    if (pdl) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        prefetch_map();
+    }
+    if (kFusedLabels) {
         if (c < cols) labels[base + c] = label;
     } else {
         label = c < cols ? labels[base + c] : 0;
@@ -376,26 +390,47 @@ void launch_frame_map(const double *cloud, const int *labels, const RowMap &map,
     k_frame_map<<<n_seq * rows * tiles, kTile, 0, stream>>>(cloud, labels, map, poses, rows, cols, tiles);
 }
 
+template <bool kFusedLabels, bool kFuseMap>
+static void launch_match_variant(int grid, cudaStream_t stream, bool pdl, const double *cloud, int *labels,
+                                 const RowMap &map, const MatchOut &out, const PoseBatch &poses, int rows, int cols,
+                                 int tiles, unsigned *n_exact, const RowMap &map_next, const PoseBatch &final_poses) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kTile);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k_frame_match<kFusedLabels, kFuseMap>, cloud, labels, map, out, poses, rows, cols, tiles,
+                       n_exact, map_next, final_poses, pdl ? 1 : 0);
+}
+
+// pdl: launch with programmatic stream serialisation, so that consecutive frame launches on one stream
+// overlap (the next frame's stencil phase runs under this frame's tail).  Safe next to any other work
+// on the stream: only k_frame_match itself releases its dependents early, and only this kernel's
+// cloud-reading phase runs in front of the dependency wait.
 void launch_frame_match(const double *cloud, int *labels, bool fused_labels, const RowMap &map,
                         const MatchOut &out, const PoseBatch &poses, int n_seq, int rows, int cols,
                         unsigned *n_exact, cudaStream_t stream, const RowMap *map_next,
-                        const PoseBatch *final_poses) {
+                        const PoseBatch *final_poses, bool pdl) {
     const int tiles = div_up(cols, kTile);
     const int grid = n_seq * rows * tiles;
     if (map_next && final_poses) {
         if (fused_labels)
-            k_frame_match<true, true><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles,
-                                                                  n_exact, *map_next, *final_poses);
+            launch_match_variant<true, true>(grid, stream, pdl, cloud, labels, map, out, poses, rows, cols, tiles,
+                                             n_exact, *map_next, *final_poses);
         else
-            k_frame_match<false, true><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles,
-                                                                   n_exact, *map_next, *final_poses);
+            launch_match_variant<false, true>(grid, stream, pdl, cloud, labels, map, out, poses, rows, cols, tiles,
+                                              n_exact, *map_next, *final_poses);
     } else {
         if (fused_labels)
-            k_frame_match<true, false><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles,
-                                                                   n_exact, map, poses);
+            launch_match_variant<true, false>(grid, stream, pdl, cloud, labels, map, out, poses, rows, cols, tiles,
+                                              n_exact, map, poses);
         else
-            k_frame_match<false, false><<<grid, kTile, 0, stream>>>(cloud, labels, map, out, poses, rows, cols, tiles,
-                                                                    n_exact, map, poses);
+            launch_match_variant<false, false>(grid, stream, pdl, cloud, labels, map, out, poses, rows, cols, tiles,
+                                               n_exact, map, poses);
     }
 }
 
