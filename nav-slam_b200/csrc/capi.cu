@@ -1005,8 +1005,12 @@ extern "C" int nav_frontend_frame_async(nav_ctx *c, const nav_point *cloud, cons
     const bool packed = feature_out && nn_idx_out == feature_out + c->ntot &&
                         (void *)nn_dist_out == (void *)(nn_idx_out + c->ntot) &&
                         (void *)global_out == (void *)(nn_dist_out + c->ntot);
+    const bool packed3 = !global_out && feature_out && nn_idx_out == feature_out + c->ntot &&
+                         (void *)nn_dist_out == (void *)(nn_idx_out + c->ntot);
     if (packed) {
         CU(cudaMemcpyAsync(feature_out, sl.d_labels, c->ntot * 40, cudaMemcpyDeviceToHost, c->s_out));
+    } else if (packed3) {  // labels | idx | dist adjacent, the mapped cloud stays in HBM
+        CU(cudaMemcpyAsync(feature_out, sl.d_labels, c->ntot * 16, cudaMemcpyDeviceToHost, c->s_out));
     } else {
         if (feature_out) CU(cudaMemcpyAsync(feature_out, sl.d_labels, c->ntot * 4, cudaMemcpyDeviceToHost, c->s_out));
         if (nn_idx_out) CU(cudaMemcpyAsync(nn_idx_out, sl.d_nn_idx, c->ntot * 4, cudaMemcpyDeviceToHost, c->s_out));
