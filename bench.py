@@ -520,15 +520,11 @@ def run_gpu_arm(args):
         buf_i = torch.empty(nq, dtype=torch.int32, device="cuda")
         buf_d = torch.empty(nq, dtype=torch.float64, device="cuda")
 
-        def nn_fn(qs):   # this rank's shard of the queries, results into preallocated buffers
-            m = int(qs.shape[0])
-            tree.nn_batch_dev(qs.data_ptr(), m, buf_i.data_ptr(), buf_d.data_ptr(), s)
-            return buf_i[:m], buf_d[:m]
+        def nn_into(qs, idx_view, dist_view):   # this rank's shard of the queries, answers written in place
+            tree.nn_batch_dev(qs.data_ptr(), int(qs.shape[0]), idx_view.data_ptr(), dist_view.data_ptr(), s)
 
         def nn_step():
-            if world == 1:
-                return nn_fn(d_q)
-            return sharding.sharded_nn(nn_fn, d_q)
+            return sharding.sharded_nn_into(nn_into, d_q, buf_i, buf_d)
 
         spin_up()
         for _ in range(3):

@@ -69,6 +69,35 @@ def sharded_nn(nn_fn: Callable, queries, *, group=None, device=None):
     return idx, dd
 
 
+def sharded_nn_into(nn_into: Callable, queries, idx_out, dist_out, *, group=None):
+    """The same exchange without any packing work, for the hot loop: idx_out [nq] int32 and dist_out [nq]
+    float64 are preallocated on the collective's device (same shapes on every rank); nn_into(q_shard,
+    idx_view, dist_view) writes this rank's contiguous shard straight into its slice of them, and two
+    in-place all_gathers (the slice is the rank's send buffer) complete both arrays on every rank.
+    Needs equal shards (nq % world == 0); otherwise the padded path of sharded_nn() is used."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    nq = int(queries.shape[0])
+    lo, hi = shard_bounds(nq, world, rank)
+    if world > 1 and nq % world != 0:
+        def nn_fn(qs):
+            m = int(qs.shape[0])
+            nn_into(qs, idx_out[lo:lo + m], dist_out[lo:lo + m])
+            return idx_out[lo:lo + m].clone(), dist_out[lo:lo + m].clone()
+        i, d = sharded_nn(nn_fn, queries, group=group)
+        idx_out.copy_(i)
+        dist_out.copy_(d)
+        return idx_out, dist_out
+    nn_into(queries[lo:hi], idx_out[lo:hi], dist_out[lo:hi])
+    if world > 1:
+        on_cpu = idx_out.device.type == "cpu"   # gloo wants distinct send / receive storage
+        dist.all_gather_into_tensor(idx_out, idx_out[lo:hi].clone() if on_cpu else idx_out[lo:hi], group=group)
+        dist.all_gather_into_tensor(dist_out, dist_out[lo:hi].clone() if on_cpu else dist_out[lo:hi], group=group)
+    return idx_out, dist_out
+
+
 def broadcast_points(points, *, src: int = 0, group=None):
     """Replicate the map points (torch tensor [n,3] float64 on the collective's device)."""
     import torch.distributed as dist

@@ -40,6 +40,24 @@ def main():
     ref_i, ref_d = oracle.nn_brute(pts.numpy(), q.numpy())
     assert np.array_equal(idx.numpy(), ref_i) and np.array_equal(dd.numpy(), ref_d)
 
+    # the in-place exchange of the hot loop: equal shards (two all_gathers, no packing) and the ragged case
+    for nq2 in (1000, 1001):
+        q2 = q[:nq2].contiguous()
+        idx_full = torch.full((nq2,), -7, dtype=torch.int32)
+        dist_full = torch.full((nq2,), -7.0, dtype=torch.float64)
+        seen = []
+
+        def nn_into(qs, iv, dv):
+            seen.append(int(qs.shape[0]))
+            i, d = oracle.nn_brute(pts.numpy(), qs.numpy())
+            iv.copy_(torch.from_numpy(i))
+            dv.copy_(torch.from_numpy(d))
+
+        sharding.sharded_nn_into(nn_into, q2, idx_full, dist_full)
+        a, b = sharding.shard_bounds(nq2, world, rank)
+        assert seen == [b - a], seen
+        assert np.array_equal(idx_full.numpy(), ref_i[:nq2]) and np.array_equal(dist_full.numpy(), ref_d[:nq2])
+
     # independent sequences: every rank processes its own, results meet on the host
     mine = sharding.assign_sequences(5, world)[rank]
     local = [(s, np.full(6, float(s))) for s in mine]
