@@ -34,6 +34,8 @@
 // index on ties.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include <math.h>
 #include <stdlib.h>
@@ -134,20 +136,21 @@ __global__ void k_mark(const int *__restrict__ lists, int n, int level, const un
     }
 }
 
-// the three lists are handled as one array of 3n positions (list a = positions [a*n, (a+1)*n))
-__global__ void k_flags(const int *__restrict__ lists, int n, const int *__restrict__ seg_lo,
-                        const unsigned char *__restrict__ side, unsigned long long *__restrict__ flags) {
-    const long long base = (long long)blockIdx.y * n;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        const long long g = base + p;
-        unsigned long long f = 0;
-        if (seg_lo[p] >= 0) {
-            const unsigned char s = side[lists[g]];
-            f = s == 0 ? 1ull : (s == 1 ? (1ull << 32) : 0ull);
-        }
-        flags[g] = f;
+// the three lists are handled as one array of 3n positions (list a = positions [a*n, (a+1)*n)).
+// Input of the prefix sum, evaluated on the fly by the scan kernel (no flag array is materialised):
+// packed counters, low word = "goes left", high word = "is the median", of the point at position g.
+struct SideFlag {
+    const int *lists;
+    const int *seg_lo;
+    const unsigned char *side;
+    long long n;
+    __device__ __forceinline__ unsigned long long operator()(long long g) const {
+        const long long p = g < n ? g : (g < 2 * n ? g - n : g - 2 * n);
+        if (seg_lo[p] < 0) return 0ull;
+        const unsigned char sd = side[lists[g]];
+        return sd == 0 ? 1ull : (sd == 1 ? (1ull << 32) : 0ull);
     }
-}
+};
 
 __global__ void k_scatter(const int *__restrict__ lists, int *__restrict__ lists_out, int n,
                           const int *__restrict__ seg_lo, const int *__restrict__ seg_mid,
@@ -187,6 +190,180 @@ __global__ void k_emit_nodes(const double *__restrict__ pts, const int *__restri
         nd.idx = i;
         nd.axis = axis_at[p];
         nodes[p] = nd;
+    }
+}
+
+// ---- finisher: once every segment of a level holds at most kFinSeg points, one CTA takes one segment
+// and builds the whole subtree below it in shared memory -- the same choose / mark / stable partition
+// steps as the global levels, with __syncthreads() where those have kernel boundaries -- and writes the
+// finished nodes.  Replaces the last ~11 levels (5 launches and several passes over all 3n list entries
+// each) by one launch.
+constexpr int kFinSeg = 2048;
+constexpr int kFinThreads = 512;
+constexpr int kFinItems = kFinSeg / kFinThreads;
+// lists (2 x 3 x int) + prefix sums + global ids + split axes + side codes
+constexpr size_t kFinSmemBytes = sizeof(int) * 6 * kFinSeg + sizeof(unsigned) * kFinSeg + sizeof(int) * kFinSeg + 2 * kFinSeg;
+
+// nodes created by the global levels (depth < level0): thread j in [1, 2^level0) is segment j - 2^L of level L
+__global__ void k_emit_top(const double *__restrict__ pts, const int *__restrict__ list0, int n, int level0,
+                           const unsigned char *__restrict__ axis_at, KdNode *__restrict__ nodes) {
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (j < 1 || j >= (1ll << level0)) return;
+    const int L = 63 - __clzll(j);
+    int lo, hi;
+    if (!segment_range((int)(j - (1ll << L)), n, L, lo, hi)) return;
+    const int mid = lo + ((hi - lo) >> 1);
+    const int i = list0[mid];
+    KdNode nd;
+    nd.x = pts[(long long)i * 3];
+    nd.y = pts[(long long)i * 3 + 1];
+    nd.z = pts[(long long)i * 3 + 2];
+    nd.idx = i;
+    nd.axis = axis_at[mid];
+    nodes[mid] = nd;
+}
+
+__global__ void __launch_bounds__(kFinThreads, 3)
+k_kd_finish(const double *__restrict__ pts, const int *__restrict__ lists_in, int n, int level0, int split_rule,
+            int *__restrict__ loc, KdNode *__restrict__ nodes) {
+    extern __shared__ __align__(16) unsigned char fin_smem[];
+    int *cur = reinterpret_cast<int *>(fin_smem);        // [3][kFinSeg]
+    int *alt = cur + 3 * kFinSeg;                         // [3][kFinSeg]
+    unsigned *sc = reinterpret_cast<unsigned *>(alt + 3 * kFinSeg);  // [kFinSeg] exclusive prefix, lefts | meds << 16
+    int *gid = reinterpret_cast<int *>(sc + kFinSeg);    // [kFinSeg] local id -> index of the point in the build input
+    unsigned char *ax = reinterpret_cast<unsigned char *>(gid + kFinSeg);  // [kFinSeg] split axis of the node at a position
+    unsigned char *side = ax + kFinSeg;                   // [kFinSeg] left / median / right code per local id
+    __shared__ unsigned s_wsum[kFinThreads / 32];
+    int LO, HI;
+    if (!segment_range((int)blockIdx.x, n, level0, LO, HI)) return;
+    const int m = HI - LO;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // local ids: the i-th entry of the x-sorted list is point i of this CTA; `loc` (n ints of global
+    // scratch, each CTA touches only its own points) translates the two other lists once, after which
+    // every level works on shared memory only
+    for (int i = tid; i < m; i += kFinThreads) {
+        const int g = lists_in[LO + i];
+        gid[i] = g;
+        loc[g] = i;
+        cur[i] = i;
+    }
+    for (int i = tid; i < kFinSeg; i += kFinThreads) ax[i] = 0;
+    __syncthreads();
+    for (int d = 1; d < 3; ++d)
+        for (int i = tid; i < m; i += kFinThreads) cur[d * kFinSeg + i] = loc[lists_in[(long long)d * n + LO + i]];
+    // this thread owns positions 4*tid .. 4*tid+3 (relative to LO); lo_r/hi_r: their current segment,
+    // hi_r < 0 once the position has become a node
+    int lo_r[kFinItems], hi_r[kFinItems];
+#pragma unroll
+    for (int k = 0; k < kFinItems; ++k) {
+        lo_r[k] = 0;
+        hi_r[k] = (kFinItems * tid + k < m) ? m : -1;
+    }
+    __syncthreads();
+    for (int l = 0; (m >> l) >= 2; ++l) {
+        // choose: one thread per segment of this level
+        for (int sgm = tid; sgm < (1 << l); sgm += kFinThreads) {
+            int lo, hi;
+            if (!segment_range(sgm, m, l, lo, hi)) continue;
+            int axis = (level0 + l) % 3;
+            if (split_rule == kSplitWidest) {
+                double ext[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const double first = pts[(long long)gid[cur[d * kFinSeg + lo]] * 3 + d];
+                    const double last = pts[(long long)gid[cur[d * kFinSeg + hi - 1]] * 3 + d];
+                    ext[d] = last - first;
+                }
+                axis = 0;
+                if (ext[1] > ext[axis]) axis = 1;
+                if (ext[2] > ext[axis]) axis = 2;
+            }
+            ax[lo + ((hi - lo) >> 1)] = (unsigned char)axis;
+        }
+        __syncthreads();
+        // mark: left / median / right of every point, read off the list of its segment's split axis
+#pragma unroll
+        for (int k = 0; k < kFinItems; ++k) {
+            if (hi_r[k] < 0) continue;
+            const int p = kFinItems * tid + k, mid = lo_r[k] + ((hi_r[k] - lo_r[k]) >> 1);
+            side[cur[ax[mid] * kFinSeg + p]] = p < mid ? 0 : (p == mid ? 1 : 2);
+        }
+        __syncthreads();
+        // stable partition of the three lists inside every segment
+        for (int d = 0; d < 3; ++d) {
+            unsigned f[kFinItems], run = 0;
+            int idv[kFinItems];
+            unsigned char sdv[kFinItems];
+#pragma unroll
+            for (int k = 0; k < kFinItems; ++k) {
+                const int p = kFinItems * tid + k;
+                idv[k] = p < m ? cur[d * kFinSeg + p] : 0;
+                sdv[k] = 3;
+                f[k] = 0;
+                if (hi_r[k] >= 0) {
+                    sdv[k] = side[idv[k]];
+                    f[k] = sdv[k] == 0 ? 1u : (sdv[k] == 1 ? (1u << 16) : 0u);
+                }
+                run += f[k];
+            }
+            unsigned inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) s_wsum[warp] = inc;
+            __syncthreads();
+            unsigned base = 0;
+            for (int w = 0; w < warp; ++w) base += s_wsum[w];
+            unsigned ex = base + inc - run;
+#pragma unroll
+            for (int k = 0; k < kFinItems; ++k) {
+                sc[kFinItems * tid + k] = ex;
+                ex += f[k];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kFinItems; ++k) {
+                const int p = kFinItems * tid + k;
+                if (p >= m) continue;
+                if (hi_r[k] < 0) {
+                    alt[d * kFinSeg + p] = idv[k];
+                    continue;
+                }
+                const int lo = lo_r[k], mid = lo + ((hi_r[k] - lo) >> 1);
+                const unsigned rel = sc[p] - sc[lo];
+                const int lefts = (int)(rel & 0xffffu), meds = (int)(rel >> 16);
+                const int dst = sdv[k] == 0 ? lo + lefts : (sdv[k] == 1 ? mid : mid + 1 + ((p - lo) - lefts - meds));
+                alt[d * kFinSeg + dst] = idv[k];
+            }
+            __syncthreads();
+        }
+        // descend: every position moves into the child segment that contains it
+#pragma unroll
+        for (int k = 0; k < kFinItems; ++k) {
+            if (hi_r[k] < 0) continue;
+            const int p = kFinItems * tid + k, mid = lo_r[k] + ((hi_r[k] - lo_r[k]) >> 1);
+            if (p < mid)
+                hi_r[k] = mid;
+            else if (p == mid)
+                hi_r[k] = -1;
+            else
+                lo_r[k] = mid + 1;
+        }
+        int *t2 = cur;
+        cur = alt;
+        alt = t2;
+    }
+    for (int p = tid; p < m; p += kFinThreads) {
+        const int i = gid[cur[p]];
+        KdNode nd;
+        nd.x = pts[(long long)i * 3];
+        nd.y = pts[(long long)i * 3 + 1];
+        nd.z = pts[(long long)i * 3 + 2];
+        nd.idx = i;
+        nd.axis = ax[p];
+        nodes[LO + p] = nd;
     }
 }
 
@@ -237,7 +414,11 @@ cudaError_t kd_build(const double *d_pts, size_t n_sz, KdNode *d_nodes, double *
     KD_CHECK(cudaMallocAsync(&axis_at, n_sz, stream));
     KD_CHECK(cudaMemsetAsync(axis_at, 0, n_sz, stream));
     KD_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys, keys_alt, idx0, lists, n, 0, 64, stream));
-    KD_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, flags, flags, 3ll * n, stream));
+    {
+        auto flag_in = thrust::make_transform_iterator(thrust::counting_iterator<long long>(0),
+                                                       SideFlag{lists, seg_lo, side, (long long)n});
+        KD_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, flag_in, flags, 3ll * n, stream));
+    }
     tmp_bytes = tmp_sort > tmp_scan ? tmp_sort : tmp_scan;
     KD_CHECK(cudaMallocAsync(&tmp, tmp_bytes, stream));
 
@@ -255,20 +436,40 @@ cudaError_t kd_build(const double *d_pts, size_t n_sz, KdNode *d_nodes, double *
     {
         int *cur = lists, *alt = lists_alt;
         const dim3 grid3((unsigned)grid, 3u);  // blockIdx.y = list
-        for (int level = 0; (n >> level) >= 2; ++level) {
+        // global levels until every segment fits one CTA of the finisher
+        int level0 = 0;
+        while ((n >> level0) > kFinSeg) ++level0;
+        for (int level = 0; level < level0; ++level) {
             long long sgrid = ((1ll << level) + threads - 1) / threads;
             if (sgrid > grid) sgrid = grid;
             k_choose_axis<<<(int)sgrid, threads, 0, stream>>>(d_pts, cur, n, level, split_rule, axis_at);
             k_mark<<<grid, threads, 0, stream>>>(cur, n, level, axis_at, seg_lo, seg_mid, side);
-            k_flags<<<grid3, threads, 0, stream>>>(cur, n, seg_lo, side, flags);
-            KD_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_scan, flags, flags, 3ll * n, stream));
+            auto flag_in = thrust::make_transform_iterator(thrust::counting_iterator<long long>(0),
+                                                           SideFlag{cur, seg_lo, side, (long long)n});
+            KD_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_scan, flag_in, flags, 3ll * n, stream));
             k_scatter<<<grid3, threads, 0, stream>>>(cur, alt, n, seg_lo, seg_mid, side, flags);
-            nl += 6;
+            nl += 5;
             int *t2 = cur;
             cur = alt;
             alt = t2;
         }
-        k_emit_nodes<<<grid, threads, 0, stream>>>(d_pts, cur, n, axis_at, d_nodes);
+        if (level0 > 0) {
+            const long long tn = 1ll << level0;
+            k_emit_top<<<(unsigned)((tn + threads - 1) / threads), threads, 0, stream>>>(d_pts, cur, n, level0, axis_at,
+                                                                                         d_nodes);
+            ++nl;
+        }
+        static bool fin_configured = false;  // per process; the attribute is per device function and device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        static int fin_dev_mask = 0;
+        if (!fin_configured || !(fin_dev_mask & (1 << (dev & 31)))) {
+            KD_CHECK(cudaFuncSetAttribute(k_kd_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemBytes));
+            fin_configured = true;
+            fin_dev_mask |= 1 << (dev & 31);
+        }
+        k_kd_finish<<<1u << level0, kFinThreads, kFinSmemBytes, stream>>>(d_pts, cur, n, level0, split_rule, seg_lo,
+                                                                           d_nodes);
         ++nl;
     }
     KD_CHECK(cudaGetLastError());
