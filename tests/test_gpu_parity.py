@@ -373,7 +373,7 @@ def _check_inorder(nodes, axes, lo, hi, depth, split):
 
 @pytest.mark.parametrize("split", ["widest", "cyclic"])
 @pytest.mark.parametrize("kind", ["uniform", "clustered", "integer", "duplicates", "sorted", "all_equal", "planes"])
-@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 1000, 30000])
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 1000, 2049, 4096, 30000])
 def test_kdtree_exact_lowest_index(pkg, oracle, synth, kind, n, split):
     rng = np.random.default_rng(n + 13)
     if kind == "uniform":
