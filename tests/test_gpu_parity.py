@@ -576,3 +576,67 @@ def test_csv_rows_gpu_resident_cloud_and_host_fallback(pkg, oracle, synth):
         assert got == oracle.csv_format_frame(5, g, huge_pose)
     finally:
         ctx.close()
+
+
+# ------------------------------------------------- device-resident sequence replay (bench `value`) ----
+def _dev_to_numpy(torch, ptr, dtype, count):
+    """Copy `count` elements from a raw device pointer (results owned by the context) to numpy."""
+    import ctypes
+    out = np.empty(count, dtype=dtype)
+    cudart = ctypes.CDLL("libcudart.so")
+    rc = cudart.cudaMemcpy(ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(ptr), ctypes.c_size_t(out.nbytes),
+                           ctypes.c_int(2))  # cudaMemcpyDeviceToHost
+    assert rc == 0, rc
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,n_seq,n_frames", [((64, 2048), 1, 12), ((16, 1800), 1, 9), ((5, 33), 1, 6),
+                                                   ((16, 1800), 3, 5)])
+def test_sequence_dev_matches_oracle(pkg, oracle, synth, shape, n_seq, n_frames):
+    """nav_frontend_sequence_dev: one launch per frame, consecutive launches overlapped by programmatic
+    dependent launch.  Stopping the replay after k frames must leave exactly what the oracle has after k
+    frames (labels, NN index / distance of frame k and the mapped cloud), for several k -- a hazard
+    between overlapping launches would corrupt an intermediate map and show up in a later frame."""
+    torch = pytest.importorskip("torch")
+    r, c = shape
+    npx = r * c
+    frames = np.stack([np.stack([synth.room_frame(r, c, f, seq=s) for s in range(n_seq)]) for f in range(n_frames)])
+    d_frames = torch.from_numpy(frames).cuda()                      # [frame][seq][r][c][3]
+    stream = torch.cuda.Stream()
+    pos0 = np.zeros((n_seq, 6))
+    pred = np.stack([np.stack([np.array([50.0 * f - 1.0, 1.0 + s, 0, 0, 0, 0.2]) for s in range(n_seq)])
+                     for f in range(n_frames)])
+    final = np.stack([np.stack([np.array([50.0 * f, 0.5 * s, 0, 0, 0, 0.0]) for s in range(n_seq)])
+                      for f in range(n_frames)])
+    last = np.concatenate([pos0[None], final[:-1]])
+    slams = [oracle.slam(r, c, 1) for _ in range(n_seq)]
+    for s in range(n_seq):
+        slams[s].init(pos0[s], frames[0, s])
+    want = {}
+    for f in range(1, n_frames):
+        want[f] = [slams[s].frontend_frame(frames[f, s], pred[f, s], last[f, s], final[f, s]) for s in range(n_seq)]
+    ctx = pkg.Context(r, c, device=0, n_seq=n_seq)
+    try:
+        ctx.set_stream(stream.cuda_stream)
+        for k in sorted({1, 2, n_frames // 2, n_frames - 1}):
+            ctx.slam_init_dev(d_frames[0].data_ptr(), pos0)
+            ctx.frontend_sequence_dev(d_frames[1].data_ptr(), k, pred[1:k + 1].reshape(-1, 6),
+                                      last[1:k + 1].reshape(-1, 6), final[1:k + 1].reshape(-1, 6))
+            stream.synchronize()
+            res = ctx.frame_results_dev()
+
+            labels = _dev_to_numpy(torch, res.labels, np.int32, n_seq * npx).reshape(n_seq, r, c)
+            idx = _dev_to_numpy(torch, res.nn_idx, np.int32, n_seq * npx).reshape(n_seq, r, c)
+            dist = _dev_to_numpy(torch, res.nn_dist, np.float64, n_seq * npx).reshape(n_seq, r, c)
+            glob = _dev_to_numpy(torch, res.global_, np.float64, n_seq * npx * 3).reshape(n_seq, r, c, 3)
+            for s in range(n_seq):
+                ofeat, oidx, odist, og = want[k][s]
+                lab = ofeat == 1
+                assert np.array_equal(labels[s], ofeat), (k, s)
+                assert np.array_equal(idx[s][lab], oidx[lab]) and np.array_equal(dist[s][lab], odist[lab]), (k, s)
+                assert np.array_equal(glob[s], og), (k, s)
+    finally:
+        ctx.close()
+        for sl in slams:
+            sl.close()
