@@ -218,10 +218,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // neighbour there), and the super boxes of the whole row
 constexpr int kNbLeaves = kChunksPerSuper + 2;
 constexpr int kMaxSuperSmem = 64;  // rows wider than 64*256 columns read the super boxes from global memory
+constexpr int kMaxRowLeafSmem = 128;  // leaf boxes of the whole row (rows up to 2048 columns); wider rows use global memory
 struct MapSmem {
     double pts[kNbLeaves * kChunk * 3];
     float4 box[kNbLeaves * 2];
     float4 sbox[kMaxSuperSmem * 2];
+    float4 rbox[kMaxRowLeafSmem * 2];
     unsigned mask[kNbLeaves];
 };
 
@@ -268,6 +270,9 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
         } else if (threadIdx.x >= 128 && (int)threadIdx.x < 128 + 2 * min(n_sup, kMaxSuperSmem)) {
             cp_async16(&sm.sbox[threadIdx.x - 128], m_sbox + (threadIdx.x - 128));
         }
+        // every leaf box of the row: a query near the edge of its tile (or far from its neighbour) tests
+        // the leaves of other super blocks too, and sixteen dependent global loads made those warps the tail
+        if (n_leaf <= kMaxRowLeafSmem && (int)threadIdx.x < 2 * n_leaf) cp_async16(&sm.rbox[threadIdx.x], m_box + threadIdx.x);
     };
     // Programmatic dependent launch (pdl != 0, kernel launched with the stream-serialisation attribute):
     // the next frame's launch may start while this one still runs.  Everything in front of
@@ -330,7 +335,7 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
     const PoseXf &pose = poses.p[seq];
     const P3 q = shift_point(pose, xf_point(pose, p));
     const Q32 q32 = make_q32(q);
-    const bool sup_in_smem = n_sup <= kMaxSuperSmem;
+    const bool sup_in_smem = n_sup <= kMaxSuperSmem, row_in_smem = n_leaf <= kMaxRowLeafSmem;
 
     double best = INFINITY;
     float best_up = INFINITY;  // float(best) rounded up
@@ -350,8 +355,8 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
             const int lf = seed + sgn * d, j = lf - leaf0;
             if (lf < 0 || lf >= n_leaf) continue;
             const bool near_leaf = j >= 0 && j < kNbLeaves;
-            const float4 blo = near_leaf ? sm.box[j * 2] : __ldg(m_box + lf * 2);
-            const float4 bhi = near_leaf ? sm.box[j * 2 + 1] : __ldg(m_box + lf * 2 + 1);
+            const float4 blo = row_in_smem ? sm.rbox[lf * 2] : (near_leaf ? sm.box[j * 2] : __ldg(m_box + lf * 2));
+            const float4 bhi = row_in_smem ? sm.rbox[lf * 2 + 1] : (near_leaf ? sm.box[j * 2 + 1] : __ldg(m_box + lf * 2 + 1));
             if (box_lower_bound32(blo, bhi, q32) > best_up) continue;
             if (near_leaf)
                 scan_leaf(sm.pts + j * kChunk * 3, sm.mask[j], lf * kChunk, q, best, bcol);
@@ -366,6 +371,42 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
         const float4 shi = sup_in_smem ? sm.sbox[sc * 2 + 1] : __ldg(m_sbox + sc * 2 + 1);
         if (box_lower_bound32(slo, shi, q32) > best_up) continue;
         const int l1 = min(n_leaf, (sc + 1) * kChunksPerSuper);
+        if (row_in_smem) {
+            // all leaf boxes of the row sit in shared memory: the sixteen lower bounds of a super block are
+            // evaluated as independent chains, four at a time, into a bit mask -- instead of sixteen
+            // dependent test-and-branch rounds -- and only the leaves that pass are visited (and re-tested
+            // against the then-current best)
+            const int l0 = sc * kChunksPerSuper;
+            unsigned pass = 0;
+#pragma unroll
+            for (int g = 0; g < kChunksPerSuper; g += 4) {
+                float lb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int lf = min(l0 + g + i, n_leaf - 1);
+                    lb[i] = box_lower_bound32(sm.rbox[lf * 2], sm.rbox[lf * 2 + 1], q32);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pass |= (unsigned)!(lb[i] > best_up) << (g + i);
+            }
+            // drop the leaves visited above and those beyond the end of the row
+            for (int d = -kNear; d <= kNear; ++d) {
+                const int j = seed + d - l0;
+                if (j >= 0 && j < kChunksPerSuper) pass &= ~(1u << j);
+            }
+            if (l1 - l0 < kChunksPerSuper) pass &= (1u << (l1 - l0)) - 1u;
+            while (pass) {
+                const int lf = l0 + __ffs(pass) - 1, j = lf - leaf0;
+                pass &= pass - 1;
+                if (box_lower_bound32(sm.rbox[lf * 2], sm.rbox[lf * 2 + 1], q32) > best_up) continue;
+                if (j >= 0 && j < kNbLeaves)
+                    scan_leaf(sm.pts + j * kChunk * 3, sm.mask[j], lf * kChunk, q, best, bcol);
+                else
+                    scan_leaf(m_pts + (long long)lf * kChunk * 3, __ldg(m_mask + lf), lf * kChunk, q, best, bcol);
+                best_up = __double2float_ru(best);
+            }
+            continue;
+        }
         for (int lf = sc * kChunksPerSuper; lf < l1; ++lf) {
             if (lf >= seed - kNear && lf <= seed + kNear) continue;  // already visited
             const int j = lf - leaf0;
