@@ -54,13 +54,19 @@ __device__ __forceinline__ void store_p3(double *__restrict__ p, const P3 &v) {
     p[2] = v.z;
 }
 
-// min/max over the 16 lanes of a half warp
-__device__ __forceinline__ void half_minmax(double &lo, double &hi) {
-#pragma unroll
-    for (int d = 8; d >= 1; d >>= 1) {
-        lo = fmin(lo, __shfl_xor_sync(kFull, lo, d, 16));
-        hi = fmax(hi, __shfl_xor_sync(kFull, hi, d, 16));
-    }
+// min / max over the 16 lanes of a half warp with one redux.sync each: floats compare like their
+// order-preserving integer images (non-negative floats as they are, negative ones with the magnitude
+// bits flipped), so an integer min / max over the half warp is the float min / max
+__device__ __forceinline__ int float_order_key(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float float_from_order_key(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+__device__ __forceinline__ float half_min(float v, unsigned half_mask) {
+    return float_from_order_key(__reduce_min_sync(half_mask, float_order_key(v)));
+}
+__device__ __forceinline__ float half_max(float v, unsigned half_mask) {
+    return float_from_order_key(__reduce_max_sync(half_mask, float_order_key(v)));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -77,20 +83,18 @@ __device__ __forceinline__ void map_tile(bool lab, bool valid, const P3 &p, cons
     }
     const unsigned ballot = __ballot_sync(kFull, lab);
     const unsigned mask16 = (ballot >> (half * 16)) & 0xffffu;
-    double lo[3], hi[3];
-    lo[0] = lab ? g.x : INFINITY;
-    lo[1] = lab ? g.y : INFINITY;
-    lo[2] = lab ? g.z : INFINITY;
-    hi[0] = lab ? g.x : -INFINITY;
-    hi[1] = lab ? g.y : -INFINITY;
-    hi[2] = lab ? g.z : -INFINITY;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) half_minmax(lo[a], hi[a]);
+    // boxes are stored in fp32 rounded outward (see box_lower_bound32); rounding is monotone, so the
+    // min of the rounded-down coordinates is the rounded-down min (same for max / rounded up)
+    const unsigned half_mask = 0xffffu << (half * 16);
+    const float inf = __int_as_float(0x7f800000);
+    const float4 flo = make_float4(half_min(lab ? __double2float_rd(g.x) : inf, half_mask),
+                                   half_min(lab ? __double2float_rd(g.y) : inf, half_mask),
+                                   half_min(lab ? __double2float_rd(g.z) : inf, half_mask), 0.f);
+    const float4 fhi = make_float4(half_max(lab ? __double2float_ru(g.x) : -inf, half_mask),
+                                   half_max(lab ? __double2float_ru(g.y) : -inf, half_mask),
+                                   half_max(lab ? __double2float_ru(g.z) : -inf, half_mask), 0.f);
     const int leaf_in_tile = warp * 2 + half;
     const int leaf = tile * kChunksPerSuper + leaf_in_tile;
-    // boxes are stored in fp32 rounded outward (see box_lower_bound32)
-    const float4 flo = make_float4(__double2float_rd(lo[0]), __double2float_rd(lo[1]), __double2float_rd(lo[2]), 0.f);
-    const float4 fhi = make_float4(__double2float_ru(hi[0]), __double2float_ru(hi[1]), __double2float_ru(hi[2]), 0.f);
     if (l16 == 0) {
         s_lo[leaf_in_tile] = flo;
         s_hi[leaf_in_tile] = fhi;
