@@ -150,21 +150,15 @@ size_t csv_scratch_bytes(long long n) {
 
 // scratch layout: [total u64][flags u32][pad][block_off u64 x nb][block_len u32 x nb]
 int launch_csv_format(const CsvJob &job, char *d_text, void *d_scratch, cudaStream_t stream) {
-    static int configured_for = -1;
     const int nb = (int)((job.n + kCsvBlock - 1) / kCsvBlock);
     unsigned long long *total = (unsigned long long *)d_scratch;
     unsigned *flags = (unsigned *)((char *)d_scratch + 8);
     unsigned long long *block_off = (unsigned long long *)((char *)d_scratch + 16);
     unsigned *block_len = (unsigned *)(block_off + nb);
     const size_t smem = (size_t)kCsvBlock * (size_t)(kCsvHeadMax + job.tail_len);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (configured_for != dev) {
-        if (cudaFuncSetAttribute(k_csv_write, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kCsvBlock * (kCsvHeadMax + kCsvTailMax)) != cudaSuccess)
-            return 1;
-        configured_for = dev;
-    }
+    if (cudaFuncSetAttribute(k_csv_write, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             kCsvBlock * (kCsvHeadMax + kCsvTailMax)) != cudaSuccess)
+        return 1;
     if (cudaMemsetAsync(d_scratch, 0, 16, stream) != cudaSuccess) return 1;
     k_csv_len<<<nb, kCsvBlock, 0, stream>>>(job, block_len, flags);
     k_csv_scan<<<1, 1024, 0, stream>>>(block_len, nb, block_off, total);

@@ -459,15 +459,8 @@ cudaError_t kd_build(const double *d_pts, size_t n_sz, KdNode *d_nodes, double *
                                                                                          d_nodes);
             ++nl;
         }
-        static bool fin_configured = false;  // per process; the attribute is per device function and device
-        int dev = 0;
-        cudaGetDevice(&dev);
-        static int fin_dev_mask = 0;
-        if (!fin_configured || !(fin_dev_mask & (1 << (dev & 31)))) {
-            KD_CHECK(cudaFuncSetAttribute(k_kd_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemBytes));
-            fin_configured = true;
-            fin_dev_mask |= 1 << (dev & 31);
-        }
+        // opt in to > 48 KB of dynamic shared memory (per device; the call is cheap enough to repeat)
+        KD_CHECK(cudaFuncSetAttribute(k_kd_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemBytes));
         k_kd_finish<<<1u << level0, kFinThreads, kFinSmemBytes, stream>>>(d_pts, cur, n, level0, split_rule, seg_lo,
                                                                            d_nodes);
         ++nl;
