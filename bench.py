@@ -230,6 +230,27 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_near_gpu(torch, local):
+    """Pin this rank to the CPU cores next to its GPU (NVML's CPU affinity of the device) before any
+    pinned memory is allocated: first touch then places the staging buffers on the GPU's NUMA node, and
+    eight ranks do not push their PCIe traffic through one socket.  Best effort; returns the core count."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:  # noqa: BLE001 -- no NVML, no affinity API: run unbound
+        pass
+    return None
+
+
 # ------------------------------------------------------------------ GPU arm ---------------------
 def run_gpu_arm(args):
     import torch
@@ -247,6 +268,7 @@ def run_gpu_arm(args):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
+    bound_cores = bind_near_gpu(torch, local) if world > 1 else None
     pkg = load_pkg()
     if pkg.device_count() == 0:
         raise RuntimeError("bench.py: no CUDA device; the product has no CPU fallback")
@@ -604,7 +626,7 @@ def run_gpu_arm(args):
                     "blocking_call": {"value": e2e_blocking, "unit": "frames/s",
                                       "api": "nav_frontend_frame (all four outputs, returns with the results on the host)",
                                       "ms_per_step": e2e_ms / K, "wall_ms_per_step": 1e3 * e2e_wall / K}},
-            "gpu_launches": launches, "clocks": clk,
+            "gpu_launches": launches, "clocks": clk, "cpu_cores_bound_near_gpu": bound_cores,
             "roofline": None if dom is None else {
                 "kernel": {"frame_fused": "k_frame_match<fused labels, fused map>"}.get(dom, dom), "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic,
