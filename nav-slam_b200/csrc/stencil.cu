@@ -50,7 +50,10 @@ k_labels(const double *__restrict__ cloud, int *__restrict__ labels, long long n
 //     points (fp64 differences -> fp32) and exchange them with two shuffles; lanes 2..31 then decide
 //     their label (fp32 filter, exact binary64 fallback, stencil_tile.cuh).  No shared-memory round
 //     trip for the distances, 94 % lane efficiency.
-constexpr int kStages = 4;
+#ifndef NAV_STENCIL_STAGES
+#define NAV_STENCIL_STAGES 4
+#endif
+constexpr int kStages = NAV_STENCIL_STAGES;
 constexpr int kWarpOut = 30;                 // output points per warp per tile
 constexpr int kWarps = kTile / 32;           // 8 warps
 constexpr int kTileOut = kWarps * kWarpOut;  // 240 output points per tile
@@ -72,10 +75,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");  // suspend-time hint
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
