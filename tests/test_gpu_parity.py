@@ -640,3 +640,36 @@ def test_sequence_dev_matches_oracle(pkg, oracle, synth, shape, n_seq, n_frames)
         ctx.close()
         for sl in slams:
             sl.close()
+
+
+# ------------------------------------------------- odd shapes: every search path of the frame kernel ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 5), (2, 17), (3, 255), (3, 256), (3, 257), (2, 513), (2, 2049), (2, 4100),
+                                   (1, 14000)])
+@pytest.mark.parametrize("motion", ["small", "large", "scrambled"])
+def test_frontend_frame_odd_shapes(pkg, oracle, synth, shape, motion):
+    """Widths around the 16 / 256-column block sizes, rows wider than the shared-memory copy of the leaf
+    boxes (> 2048 columns; nav_create caps rows at about 14 500 columns), and motions that send queries far
+    from their own column ('large': 30 degrees of yaw; 'scrambled': the previous frame's columns are
+    permuted, so the nearest neighbour sits in an arbitrary leaf of the row)."""
+    r, c = shape
+    rng = np.random.default_rng(r * 100003 + c)
+    f0 = synth.room_frame(r, c, 0)
+    f1 = synth.room_frame(r, c, 1)
+    if motion == "scrambled":
+        f0 = np.ascontiguousarray(f0[:, rng.permutation(c)])
+    ctx = pkg.Context(r, c, device=0)
+    slam = oracle.slam(r, c, 1)
+    try:
+        z = np.zeros(6)
+        assert np.array_equal(ctx.slam_init(z, f0), slam.init(z, f0))
+        pred = np.array([50.0, 3.0, -2.0, 0.0, 0.0, 30.0 if motion == "large" else 0.3])
+        final = np.array([51.0, 2.0, -1.0, 0.1, 0.0, 0.2])
+        for cloud in (f1, synth.room_frame(r, c, 2, invalid_frac=0.02)):
+            a = ctx.frontend_frame(cloud, pred, z, final)
+            b = slam.frontend_frame(cloud, pred, z, final)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+    finally:
+        ctx.close()
+        slam.close()
