@@ -632,8 +632,8 @@ def run_gpu_arm(args):
                 "peak_source": peak_src, "unit": "GB/s", "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic,
                 "alg_bytes_per_launch": kernels[dom]["alg_bytes_per_launch"],
                 "us_per_launch": kernels[dom]["us_per_launch"],
-                "note": "one 3 MB frame per launch: bounded by latency, not HBM; the same stencil fed a batch "
-                        "reaches kernels.labels_batch.frac_of_hbm_peak"},
+                "note": "one 3 MB frame per launch: bounded by instruction issue (8.6 M warp-instructions), not by HBM; "
+                        "the same stencil fed a batch reaches kernels.labels_batch.frac_of_hbm_peak"},
             "kernels": kernels, "batched_sequences": batched, "nn": nn, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
