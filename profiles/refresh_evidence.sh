@@ -22,5 +22,8 @@ python profiles/prof_kdbuild.py > $O/r1_kdbuild.txt 2>&1
 python profiles/prof_tc.py 131072 256 1024 4096 16384 65536 > $O/r1_tc_sizes.txt 2>&1
 python profiles/prof_csv.py > $O/r1_csv_rows.txt 2>&1
 python profiles/prof_stencil.py 1000 5 > $O/r1_stencil_1000_frames.txt 2>&1
+python profiles/prof_stencil.py 256 2 > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k "regex:k_labels_tma" -s 2 -c 1 -f -o $O/stencil python profiles/prof_stencil.py 256 2 > $O/ncu_stencil.log 2>&1
+python profiles/ncu_table.py $O/stencil.ncu-rep > $O/r1_r1_stencil.txt 2>&1
+python profiles/prof_pcie.py > $O/r1_pcie.txt 2>&1
 rm -f $O/*.ncu-rep.tmp
 ls -la $O
