@@ -465,6 +465,8 @@ void launch_frame_match(const double *cloud, int *labels, bool fused_labels, con
                         const PoseBatch *final_poses, bool pdl) {
     const int tiles = div_up(cols, kTile);
     const int grid = n_seq * rows * tiles;
+    // programmatic serialisation only on ordinary streams (not the legacy / per-thread default streams)
+    pdl = pdl && stream != nullptr && stream != cudaStreamLegacy && stream != cudaStreamPerThread;
     if (map_next && final_poses) {
         if (fused_labels)
             launch_match_variant<true, true>(grid, stream, pdl, cloud, labels, map, out, poses, rows, cols, tiles,

@@ -673,3 +673,36 @@ def test_frontend_frame_odd_shapes(pkg, oracle, synth, shape, motion):
     finally:
         ctx.close()
         slam.close()
+
+
+@pytest.mark.gpu
+def test_sequence_dev_on_legacy_default_stream(pkg, oracle, synth):
+    """The sequence replay also works on the legacy default stream (no programmatic dependent launch there)."""
+    torch = pytest.importorskip("torch")
+    r, c, n = 5, 33, 5
+    frames = np.stack([synth.room_frame(r, c, f) for f in range(n)])
+    d_frames = torch.from_numpy(frames).cuda()
+    z = np.zeros(6)
+    pred = np.stack([np.array([50.0 * f - 1.0, 1.0, 0, 0, 0, 0.2]) for f in range(n)])
+    final = np.stack([np.array([50.0 * f, 0.0, 0, 0, 0, 0.0]) for f in range(n)])
+    last = np.concatenate([z[None], final[:-1]])
+    slam = oracle.slam(r, c, 1)
+    slam.init(z, frames[0])
+    for f in range(1, n):
+        want = slam.frontend_frame(frames[f], pred[f], last[f], final[f])
+    ctx = pkg.Context(r, c, device=0)
+    try:
+        ctx.set_stream(0)
+        torch.cuda.synchronize()
+        ctx.slam_init_dev(d_frames[0].data_ptr(), z)
+        ctx.frontend_sequence_dev(d_frames[1].data_ptr(), n - 1, pred[1:], last[1:], final[1:])
+        torch.cuda.synchronize()
+        res = ctx.frame_results_dev()
+        labels = _dev_to_numpy(torch, res.labels, np.int32, r * c).reshape(r, c)
+        idx = _dev_to_numpy(torch, res.nn_idx, np.int32, r * c).reshape(r, c)
+        glob = _dev_to_numpy(torch, res.global_, np.float64, r * c * 3).reshape(r, c, 3)
+        lab = want[0] == 1
+        assert np.array_equal(labels, want[0]) and np.array_equal(idx[lab], want[1][lab]) and np.array_equal(glob, want[3])
+    finally:
+        ctx.close()
+        slam.close()
