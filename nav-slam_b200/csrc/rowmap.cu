@@ -37,6 +37,7 @@ namespace nav {
 constexpr unsigned kFull = 0xffffffffu;
 #ifndef NAV_MATCH_MIN_CTAS
 #define NAV_MATCH_MIN_CTAS 4  // 64 registers/thread: keeps the fp32 query bracket live instead of re-converting it
+                              // (measured, frames/s single / 8 sequences: 3 CTAs 53.5 K / 56.2 K, 4 CTAs 58.3 K / 62.5 K, 5 CTAs 48.8 K / 63.7 K)
 #endif
 static_assert(kTile == kChunk * kChunksPerSuper, "one CTA tile = one super block of 16 leaf blocks");
 
