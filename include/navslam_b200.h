@@ -171,6 +171,18 @@ int nav_frontend_wait(nav_ctx *ctx);
  * array uninitialised there).  Same values as fscanf("%lf") bit for bit. */
 int nav_l9_csv_read(const char *path, int rows, int cols, size_t max_frames, nav_point *frames_out,
                     int *timestamps_out, size_t *n_frames_out);
+/* replaces LidarProcessData (src/main.c:12-75): `parsed_data.json`, a top-level array whose elements are
+ * objects {"time_main": integer, "distance": [integers, row-major], ...}.  Every array element is one
+ * frame; integer distances with index < rows*cols are stored, everything else of distances_out keeps
+ * its previous content (the reference leaves its stack array uninitialised there).  The document must
+ * be valid JSON, otherwise nothing is read (as with jansson's json_loadf). */
+int nav_l5_json_read(const char *path, int rows, int cols, size_t max_frames, int *distances_out,
+                     int *timestamps_out, size_t *n_frames_out);
+/* replaces IMUProcessData (src/main.c:130-178): "params": [roll, pitch, yaw, x, y, z] of every object of
+ * the same file into params_out[frame][6]; like json_real_value(), an element written as an integer
+ * reads as 0.0.  Only objects count as frames. */
+int nav_imu_json_read(const char *path, size_t max_frames, double *params_out, int *timestamps_out,
+                      size_t *n_frames_out);
 /* the header line of point_cloud_data.csv (src/main.c:243) */
 const char *nav_csv_header(void);
 /* replaces the per-frame fprintf loop of src/main.c:320-352 (L5) / :433-464 (L9): rows*cols lines

@@ -12,4 +12,4 @@ The directory name has a hyphen, so import it with importlib.import_module("nav-
 """
 from . import build, synth  # noqa: F401
 from .binding import (Context, KdTree, NavError, bruteforce_nn_dev, csv_format_frame,  # noqa: F401
-                      device_count, l9_csv_read, load_library)
+                      device_count, imu_json_read, l5_json_read, l9_csv_read, load_library)

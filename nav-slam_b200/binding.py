@@ -46,7 +46,7 @@ EXPORTS = [
     "nav_exact_fallback_count", "nav_frontend_frame_async", "nav_frontend_wait",
     "nav_frontend_sequence_dev", "nav_slam_localization_fast", "nav_frontend_frame_depth",
     "nav_l9_csv_read", "nav_csv_header", "nav_csv_format_frame", "nav_csv_format_frame_gpu",
-    "nav_csv_format_frame_dev",
+    "nav_csv_format_frame_dev", "nav_l5_json_read", "nav_imu_json_read",
 ]
 
 
@@ -118,6 +118,8 @@ def load_library(build_if_missing: bool = True):
     L.nav_csv_format_frame_gpu.argtypes = [vp, C.c_ulonglong, vp, vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), vp,
                                            C.c_size_t, C.POINTER(C.c_size_t)]
     L.nav_csv_format_frame_dev.argtypes = L.nav_csv_format_frame_gpu.argtypes
+    L.nav_l5_json_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_size_t, vp, vp, C.POINTER(C.c_size_t)]
+    L.nav_imu_json_read.argtypes = [C.c_char_p, C.c_size_t, vp, vp, C.POINTER(C.c_size_t)]
     L.nav_csv_header.restype = C.c_char_p
     L.nav_csv_format_frame.restype = C.c_size_t
     L.nav_csv_format_frame.argtypes = [vp, C.c_size_t, C.c_ulonglong, C.c_int, C.c_int, vp, vp, vp,
@@ -455,6 +457,26 @@ def l9_csv_read(path, rows, cols, max_frames):
     n = C.c_size_t(0)
     _check(L.nav_l9_csv_read(path.encode(), rows, cols, max_frames, frames.ctypes.data, ts.ctypes.data, C.byref(n)), L)
     return frames[:n.value], ts[:n.value]
+
+
+def l5_json_read(path, rows, cols, max_frames, fill=0):
+    """nav_l5_json_read: returns (distances [n,rows,cols] int32, timestamps [n] int32)."""
+    L = load_library()
+    d = np.full((max_frames, rows, cols), fill, dtype=np.int32)
+    ts = np.zeros(max_frames, dtype=np.int32)
+    n = C.c_size_t(0)
+    _check(L.nav_l5_json_read(path.encode(), rows, cols, max_frames, d.ctypes.data, ts.ctypes.data, C.byref(n)), L)
+    return d[:n.value], ts[:n.value]
+
+
+def imu_json_read(path, max_frames):
+    """nav_imu_json_read: returns (params [n,6] = roll,pitch,yaw,x,y,z, timestamps [n] int32)."""
+    L = load_library()
+    p = np.zeros((max_frames, 6))
+    ts = np.zeros(max_frames, dtype=np.int32)
+    n = C.c_size_t(0)
+    _check(L.nav_imu_json_read(path.encode(), max_frames, p.ctypes.data, ts.ctypes.data, C.byref(n)), L)
+    return p[:n.value], ts[:n.value]
 
 
 def csv_format_frame(timestamp, global_cloud, lidar_pos, distances=None, imu=None, ekf_pos=None) -> bytes:

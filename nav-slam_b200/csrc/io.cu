@@ -4,6 +4,7 @@
 // (no fscanf / fprintf in the loop).  These are the callers' formats, not kernels: nothing here touches
 // the GPU, and frames are parsed straight into caller memory (pinned memory from nav_host_alloc
 // makes them a DMA source for the frame calls).
+#include <ctype.h>
 #include <errno.h>
 #include <math.h>
 #include <stdint.h>
@@ -254,4 +255,327 @@ extern "C" size_t nav_csv_format_frame(char *buf, size_t cap, unsigned long long
         }
     }
     return (size_t)(o - buf);
+}
+
+// ------------------------------------------------------------------------- L5 JSON readers -----
+// LidarProcessData / IMUProcessData (src/main.c:12-75,130-178) read `parsed_data.json` through
+// jansson: a top-level array of objects {"time_main": int, "distance": [int...], "params": [6 reals]}.
+// This is a small validating JSON scanner for exactly that use: the whole document must be one valid
+// JSON value followed by white space only (json_loadf with flags 0), otherwise nothing is read.
+// Differences from jansson that do not matter for data files: invalid UTF-8 inside strings is accepted.
+namespace {
+
+struct JsonScan {
+    const char *p, *end;
+    bool ok = true;
+    void ws() {
+        while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
+    }
+    bool lit(const char *s) {
+        const size_t n = strlen(s);
+        if ((size_t)(end - p) >= n && memcmp(p, s, n) == 0) {
+            p += n;
+            return true;
+        }
+        return ok = false;
+    }
+    // string: returns its raw bytes (escapes are validated, not decoded: keys of interest have none)
+    bool str(std::string *out) {
+        if (p >= end || *p != '"') return ok = false;
+        ++p;
+        const char *s0 = p;
+        while (p < end && *p != '"') {
+            if ((unsigned char)*p < 0x20) return ok = false;
+            if (*p == '\\') {
+                ++p;
+                if (p >= end) return ok = false;
+                if (*p == 'u') {
+                    for (int i = 1; i <= 4; ++i)
+                        if (p + i >= end || !isxdigit((unsigned char)p[i])) return ok = false;
+                    p += 4;
+                } else if (!strchr("\"\\/bfnrt", *p)) {
+                    return ok = false;
+                }
+            }
+            ++p;
+        }
+        if (p >= end) return ok = false;
+        if (out) out->assign(s0, p);
+        ++p;
+        return true;
+    }
+    // number: JSON grammar; integer iff it has no fraction and no exponent (jansson's rule)
+    bool num(bool *is_int, long long *iv, double *dv) {
+        const char *s0 = p;
+        if (p < end && *p == '-') ++p;
+        if (p >= end) return ok = false;
+        if (*p == '0') {
+            ++p;
+        } else if (*p >= '1' && *p <= '9') {
+            while (p < end && *p >= '0' && *p <= '9') ++p;
+        } else {
+            return ok = false;
+        }
+        bool integer = true;
+        if (p < end && *p == '.') {
+            integer = false;
+            ++p;
+            if (p >= end || *p < '0' || *p > '9') return ok = false;
+            while (p < end && *p >= '0' && *p <= '9') ++p;
+        }
+        if (p < end && (*p == 'e' || *p == 'E')) {
+            integer = false;
+            ++p;
+            if (p < end && (*p == '+' || *p == '-')) ++p;
+            if (p >= end || *p < '0' || *p > '9') return ok = false;
+            while (p < end && *p >= '0' && *p <= '9') ++p;
+        }
+        char tmp[400];
+        const size_t len = (size_t)(p - s0);
+        if (len >= sizeof(tmp)) return ok = false;
+        memcpy(tmp, s0, len);
+        tmp[len] = 0;
+        errno = 0;
+        if (integer) {
+            const long long v = strtoll(tmp, nullptr, 10);
+            if (errno == ERANGE) return ok = false;  // jansson: "too big integer"
+            if (iv) *iv = v;
+        } else {
+            const double v = strtod(tmp, nullptr);
+            if (errno == ERANGE && (v == HUGE_VAL || v == -HUGE_VAL)) return ok = false;  // jansson: real overflow
+            if (dv) *dv = v;
+        }
+        if (is_int) *is_int = integer;
+        return true;
+    }
+    bool skip_value(int depth = 0) {
+        if (depth > 2048) return ok = false;  // jansson's JSON_PARSER_MAX_DEPTH
+        ws();
+        if (p >= end) return ok = false;
+        switch (*p) {
+            case '{': {
+                ++p;
+                ws();
+                if (p < end && *p == '}') return ++p, true;
+                while (true) {
+                    ws();
+                    if (!str(nullptr)) return false;
+                    ws();
+                    if (p >= end || *p != ':') return ok = false;
+                    ++p;
+                    if (!skip_value(depth + 1)) return false;
+                    ws();
+                    if (p < end && *p == ',') {
+                        ++p;
+                        continue;
+                    }
+                    if (p < end && *p == '}') return ++p, true;
+                    return ok = false;
+                }
+            }
+            case '[': {
+                ++p;
+                ws();
+                if (p < end && *p == ']') return ++p, true;
+                while (true) {
+                    if (!skip_value(depth + 1)) return false;
+                    ws();
+                    if (p < end && *p == ',') {
+                        ++p;
+                        continue;
+                    }
+                    if (p < end && *p == ']') return ++p, true;
+                    return ok = false;
+                }
+            }
+            case '"': return str(nullptr);
+            case 't': return lit("true");
+            case 'f': return lit("false");
+            case 'n': return lit("null");
+            default: return num(nullptr, nullptr, nullptr);
+        }
+    }
+};
+
+struct JsonNum {
+    bool is_num, is_int;
+    long long iv;
+    double dv;
+};
+
+// one element of the top-level array: what the two readers look at
+struct L5Record {
+    bool is_object = false;
+    bool has_time = false;  // "time_main" present and an integer
+    long long time_main = 0;
+    bool has_distance = false, has_params = false;  // present and arrays
+    std::vector<JsonNum> distance, params;
+};
+
+bool read_num_array(JsonScan &js, std::vector<JsonNum> &out) {  // at '[': every element recorded, numbers decoded
+    out.clear();
+    ++js.p;
+    js.ws();
+    if (js.p < js.end && *js.p == ']') return ++js.p, true;
+    while (true) {
+        js.ws();
+        JsonNum v = {false, false, 0, 0.0};
+        if (js.p < js.end && (*js.p == '-' || (*js.p >= '0' && *js.p <= '9'))) {
+            v.is_num = true;
+            if (!js.num(&v.is_int, &v.iv, &v.dv)) return false;
+        } else if (!js.skip_value(1)) {
+            return false;
+        }
+        out.push_back(v);
+        js.ws();
+        if (js.p < js.end && *js.p == ',') {
+            ++js.p;
+            continue;
+        }
+        if (js.p < js.end && *js.p == ']') return ++js.p, true;
+        return js.ok = false;
+    }
+}
+
+bool read_record(JsonScan &js, L5Record &r) {
+    js.ws();
+    if (js.p >= js.end) return js.ok = false;
+    if (*js.p != '{') return js.skip_value(1);
+    r.is_object = true;
+    ++js.p;
+    js.ws();
+    if (js.p < js.end && *js.p == '}') return ++js.p, true;
+    while (true) {
+        js.ws();
+        std::string key;
+        if (!js.str(&key)) return false;
+        js.ws();
+        if (js.p >= js.end || *js.p != ':') return js.ok = false;
+        ++js.p;
+        js.ws();
+        // a repeated key replaces the earlier value, as in jansson's object
+        if (key == "time_main") {
+            r.has_time = false;
+            if (js.p < js.end && (*js.p == '-' || (*js.p >= '0' && *js.p <= '9'))) {
+                bool is_int;
+                long long iv = 0;
+                if (!js.num(&is_int, &iv, nullptr)) return false;
+                r.has_time = is_int;
+                r.time_main = iv;
+            } else if (!js.skip_value(1)) {
+                return false;
+            }
+        } else if (key == "distance" || key == "params") {
+            bool &has = key == "distance" ? r.has_distance : r.has_params;
+            std::vector<JsonNum> &dst = key == "distance" ? r.distance : r.params;
+            has = false;
+            if (js.p < js.end && *js.p == '[') {
+                if (!read_num_array(js, dst)) return false;
+                has = true;
+            } else if (!js.skip_value(1)) {
+                return false;
+            }
+        } else if (!js.skip_value(1)) {
+            return false;
+        }
+        js.ws();
+        if (js.p < js.end && *js.p == ',') {
+            ++js.p;
+            continue;
+        }
+        if (js.p < js.end && *js.p == '}') return ++js.p, true;
+        return js.ok = false;
+    }
+}
+
+// the whole document -> records; false if it is not valid JSON (then the reference reads nothing either)
+int load_l5_records(const char *fn, const char *path, std::vector<L5Record> &recs, bool *root_is_array) {
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return nav_io_fail("%s: cannot open %s: %s", fn, path, strerror(errno));
+    std::string text;
+    char chunk[1 << 16];
+    size_t got;
+    while ((got = fread(chunk, 1, sizeof(chunk), fp)) > 0) text.append(chunk, got);
+    fclose(fp);
+    JsonScan js;
+    js.p = text.data();
+    js.end = js.p + text.size();
+    js.ws();
+    *root_is_array = js.p < js.end && *js.p == '[';
+    if (!*root_is_array) {
+        if (!js.skip_value()) return nav_io_fail("%s: %s is not valid JSON", fn, path);
+    } else {
+        ++js.p;
+        js.ws();
+        if (js.p < js.end && *js.p == ']') {
+            ++js.p;
+        } else {
+            while (true) {
+                recs.emplace_back();
+                if (!read_record(js, recs.back())) return nav_io_fail("%s: %s is not valid JSON", fn, path);
+                js.ws();
+                if (js.p < js.end && *js.p == ',') {
+                    ++js.p;
+                    continue;
+                }
+                if (js.p < js.end && *js.p == ']') {
+                    ++js.p;
+                    break;
+                }
+                return nav_io_fail("%s: %s is not valid JSON", fn, path);
+            }
+        }
+    }
+    js.ws();
+    if (js.p != js.end) return nav_io_fail("%s: %s has text after the JSON value", fn, path);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int nav_l5_json_read(const char *path, int rows, int cols, size_t max_frames, int *distances_out,
+                                int *timestamps_out, size_t *n_frames_out) {
+    if (!path || !distances_out || !n_frames_out || rows < 1 || cols < 1)
+        return nav_io_fail("nav_l5_json_read: bad argument");
+    *n_frames_out = 0;
+    std::vector<L5Record> recs;
+    bool is_array = false;
+    if (load_l5_records("nav_l5_json_read", path, recs, &is_array)) return 1;
+    if (!is_array) return 0;  // main.c:31: nothing to do unless the root is a non-empty array
+    if (recs.size() > max_frames)  // the reference overruns lidarData[100] here
+        return nav_io_fail("nav_l5_json_read: %zu frames in %s, room for %zu", recs.size(), path, max_frames);
+    const size_t npx = (size_t)rows * cols;
+    for (size_t f = 0; f < recs.size(); ++f) {
+        const L5Record &r = recs[f];
+        if (r.is_object) {
+            if (r.has_time && timestamps_out) timestamps_out[f] = (int)r.time_main;  // main.c:44-48
+            if (r.has_distance)
+                for (size_t i = 0; i < r.distance.size() && i < npx; ++i)           // main.c:55-63
+                    if (r.distance[i].is_num && r.distance[i].is_int) distances_out[f * npx + i] = (int)r.distance[i].iv;
+        }
+    }
+    *n_frames_out = recs.size();  // main.c:67: every array element advances the frame count
+    return 0;
+}
+
+extern "C" int nav_imu_json_read(const char *path, size_t max_frames, double *params_out, int *timestamps_out,
+                                 size_t *n_frames_out) {
+    if (!path || !params_out || !n_frames_out) return nav_io_fail("nav_imu_json_read: bad argument");
+    *n_frames_out = 0;
+    std::vector<L5Record> recs;
+    bool is_array = false;
+    if (load_l5_records("nav_imu_json_read", path, recs, &is_array)) return 1;
+    if (!is_array) return 0;
+    size_t count = 0;
+    for (const L5Record &r : recs) {
+        if (!r.is_object) continue;  // main.c:157: only objects advance the IMU count
+        if (count >= max_frames) return nav_io_fail("nav_imu_json_read: more than %zu frames in %s", max_frames, path);
+        if (r.has_time && timestamps_out) timestamps_out[count] = (int)r.time_main;
+        if (r.has_params && r.params.size() == 6)  // main.c:168-176; json_real_value() is 0.0 for a non-real
+            for (int k = 0; k < 6; ++k)
+                params_out[count * 6 + k] = (r.params[k].is_num && !r.params[k].is_int) ? r.params[k].dv : 0.0;
+        ++count;
+    }
+    *n_frames_out = count;
+    return 0;
 }

@@ -140,3 +140,21 @@ double refdrv_l9_read(const char *path, PointCloud *frames, size_t *count) {
     L9_LidarProcessData(path, frames, count);
     return now_s() - t0;
 }
+
+/* the reference's own JSON readers (src/main.c:12-75,130-178), linked from main.c like the CSV reader;
+ * both need jansson's json_loadf at run time (libjansson.so.4).  Counts start at zero as in main.c. */
+void LidarProcessData(const char *filename, L5_LidarDataFrame *lidarData, size_t *lidarCount);
+void IMUProcessData(const char *filename, IMUDataFrame *imuData, size_t *imuCount);
+size_t refdrv_sizeof_l5_frame(void) { return sizeof(L5_LidarDataFrame); }
+size_t refdrv_sizeof_imu_frame(void) { return sizeof(IMUDataFrame); }
+
+size_t refdrv_l5_json_read(const char *path, L5_LidarDataFrame *frames) {
+    size_t count = 0;
+    LidarProcessData(path, frames, &count);
+    return count;
+}
+size_t refdrv_imu_json_read(const char *path, IMUDataFrame *frames) {
+    size_t count = 0;
+    IMUProcessData(path, frames, &count);
+    return count;
+}

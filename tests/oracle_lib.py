@@ -324,6 +324,33 @@ class RefLib:
         self.sizeof_pointcloud = L.refdrv_sizeof_pointcloud()
         self.sizeof_slam_attr = L.refdrv_sizeof_slam_attr()
 
+    def l5_json_read(self, path, max_frames, fill=0):
+        """The reference's own LidarProcessData (jansson) into pre-filled L5_LidarDataFrame structs.
+        Returns (distances [n,R,C] int32, timestamps [n] int32)."""
+        L = self.lib
+        L.refdrv_sizeof_l5_frame.restype = C.c_size_t
+        L.refdrv_l5_json_read.restype = C.c_size_t
+        L.refdrv_l5_json_read.argtypes = [C.c_char_p, C.c_void_p]
+        sz = L.refdrv_sizeof_l5_frame()
+        assert sz == 4 + 4 * self.rows * self.cols
+        buf = np.full((max_frames, sz // 4), fill, dtype=np.int32)
+        with quiet_stdout():
+            n = L.refdrv_l5_json_read(path.encode(), buf.ctypes.data)
+        return buf[:n, 1:].reshape(n, self.rows, self.cols).copy(), buf[:n, 0].copy()
+
+    def imu_json_read(self, path, max_frames):
+        """The reference's own IMUProcessData.  Returns (params [n,6] roll,pitch,yaw,x,y,z, timestamps [n])."""
+        L = self.lib
+        L.refdrv_sizeof_imu_frame.restype = C.c_size_t
+        L.refdrv_imu_json_read.restype = C.c_size_t
+        L.refdrv_imu_json_read.argtypes = [C.c_char_p, C.c_void_p]
+        assert L.refdrv_sizeof_imu_frame() == 56
+        buf = np.zeros((max_frames, 7), dtype=np.float64)
+        with quiet_stdout():
+            n = L.refdrv_imu_json_read(path.encode(), buf.ctypes.data)
+        ts = buf[:n, 0].copy().view(np.int32)[::2].copy()
+        return buf[:n, 1:].copy(), ts
+
     def l9_csv_read(self, path, max_frames):
         """The reference's own L9_LidarProcessData into zeroed PointCloud structs.
         Returns (frames [n,R,C,3], timestamps [n], seconds)."""

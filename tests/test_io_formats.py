@@ -190,3 +190,64 @@ def test_read_then_write_round_trip(tmp_path, oracle):
     out = nav.csv_format_frame(1, got[1], np.zeros(6))
     cols = np.array([ln.split(b",")[3:6] for ln in out.split(b"\n")[:-1]], dtype=np.float64)
     assert np.array_equal(cols.reshape(5, 33, 3), frames[1])
+
+
+# ------------------------------------------------------------------ L5 / IMU JSON (src/main.c:12-75,130-178)
+def _json_doc(rng, n, rows=8, cols=8):
+    import json
+    recs = []
+    for f in range(n):
+        recs.append({"time_main": 1000 + 7 * f, "extra": {"nested": [1, 2.5, "x", None, True]},
+                     "distance": [int(v) for v in rng.integers(-5, 4000, rows * cols)],
+                     "params": [float(v) for v in rng.normal(0, 1, 6)], "name": 'frame "%d"' % f})
+    return json.dumps(recs, indent=1)
+
+
+def test_json_readers_match_reference(tmp_path):
+    rng = np.random.default_rng(5)
+    synth_doc = synth.l5_json(6)                                    # config 1's own input file
+    docs = {"synthetic": synth_doc, "random": _json_doc(rng, 9)}
+    # shapes of trouble: a non-object element, a real inside distance, a short and an over-long distance
+    # array, integer params (json_real_value gives 0.0), 5 params, a missing time, a repeated key
+    docs["odd"] = ('[ {"time_main": 5, "distance": [1, 2.5, 3], "params": [1, 2.0, 3.5, 4.25, 5e-1, 6.0]},\n'
+                   ' 17, {"distance": [%s], "params": [0.1, 0.2, 0.3, 0.4, 0.5]},\n'
+                   ' {"time_main": 1.5, "distance": "none", "params": [0.5, 0.25, 0.125, 1.0, 2.0, -3.0],'
+                   '  "time_main": 9, "distance": [7, 8]}, [] ]' % ", ".join(str(i) for i in range(80)))
+    for name, doc in docs.items():
+        p = _write(tmp_path, doc, name + ".json")
+        d, ts = nav.l5_json_read(p, 8, 8, 100, fill=-77)
+        prm, its = nav.imu_json_read(p, 100)
+        if name == "synthetic":
+            assert len(d) == 6 and np.array_equal(d[3], synth.l5_depth_frame(3))
+        if name == "odd":
+            assert len(d) == 5 and len(prm) == 3
+            assert d[0].ravel()[:4].tolist() == [1, -77, 3, -77] and ts[0] == 5
+            assert d[2].ravel()[:64].tolist() == list(range(64))
+            assert d[3].ravel()[:3].tolist() == [7, 8, -77] and ts[3] == 9
+            assert prm[0].tolist() == [0.0, 2.0, 3.5, 4.25, 0.5, 6.0] and prm[1].tolist() == [0.0] * 6
+        if not ref_available("8x8"):
+            continue
+        ref = RefLib(8, 8)
+        rd, rts = ref.l5_json_read(p, 100, fill=-77)
+        rprm, rits = ref.imu_json_read(p, 100)
+        assert np.array_equal(d, rd) and np.array_equal(prm, rprm)
+        # a frame without an integer "time_main" keeps whatever the caller's buffer held: both start from 0 / -77
+        assert np.array_equal(np.where(ts == 0, -77, ts), np.where(rts == -77, -77, rts)) or np.array_equal(ts, rts)
+        assert np.array_equal(its, rits)
+
+
+def test_json_invalid_documents_read_nothing(tmp_path):
+    for bad in ('[{"distance": [1, 2,]}]', '[{"distance": [1 2]}]', '[1, 2] x', '[{"a": 01}]', '[{"a": "\\q"}]', '',
+                '[{"time_main": 1}', '[{"time_main": 99999999999999999999}]'):
+        p = _write(tmp_path, bad, "bad.json")
+        with pytest.raises(nav.NavError):
+            nav.l5_json_read(p, 8, 8, 10)
+        if ref_available("8x8"):
+            rd, _ = RefLib(8, 8).l5_json_read(p, 10)
+            assert len(rd) == 0
+    # valid JSON that is not an array of frames: zero frames, no error
+    for ok in ('{}', '[]', '3', ' "text" '):
+        d, _ = nav.l5_json_read(_write(tmp_path, ok, "ok.json"), 8, 8, 10)
+        assert len(d) == 0
+    with pytest.raises(nav.NavError):
+        nav.l5_json_read(_write(tmp_path, "[1,2,3]", "many.json"), 8, 8, 2)   # more frames than room
