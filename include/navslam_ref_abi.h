@@ -89,15 +89,18 @@ void init_slam(SLAM_attr *attr, Pos pos, PointCloud *lidarPointCloud);
 Pos slam_localization(SLAM_attr *attr, PointCloud *lidarPointCloud, Pos pos_predict, Pos pos_last);
 void slam_mapping(SLAM_attr *attr, Pos pos, PointCloud *lidarPointCloud);
 
-/* un-headered externals of src/slam.c:11,64,84,95 and utils/kdtree.c:8,14 that have external
+/* un-headered externals of src/slam.c:11,64,84,95,118 and utils/kdtree.c:8,14,20 that have external
  * linkage in the reference and are natural function-level entry points */
 void extract_feature(PointCloud *lidarPointCloud, int feature[MAX_ROWS][MAX_COLS]);
 void flattenPoints(Point rowPoints[MAX_COLS], int rowFeature[MAX_COLS], Point flattenedPoints[MAX_COLS],
                    size_t *numPoints);
 void compute_posdiff(Pos *pos_now, Pos *pos_last, double pos_diff[6]);
 void getRotationMatrix(double roll, double pitch, double yaw, double R[3][3]);
+void mapCoordinatesToLastFrame(PointCloud *globalPointCloudData, double transform[3],
+                               PointCloud *positionInLastFrame);                       /* src/slam.c:118 */
 int getAxis(int depth);
 double euclideanDistance(Point p1, Point p2);
+void nth_element(Point *points, size_t first, size_t last, size_t nth, int axis);   /* utils/kdtree.c:20 */
 
 /* additions of the shim (not in the reference): batched sibling of nearestNeighborSearch and
  * access to the underlying library objects */

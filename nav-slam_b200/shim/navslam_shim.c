@@ -235,6 +235,18 @@ void getRotationMatrix(double roll, double pitch, double yaw, double R[3][3]) {
     R[2][2] = cp * cr;
 }
 
+/* src/slam.c:118-131 (un-headered helper of the reference; the frame kernel does this per query) */
+void mapCoordinatesToLastFrame(PointCloud *globalPointCloudData, double transform[3], PointCloud *positionInLastFrame) {
+    for (int row = 0; row < MAX_ROWS; ++row)
+        for (int col = 0; col < MAX_COLS; ++col) {
+            const Point *g = &globalPointCloudData->ToF_position[row][col];
+            Point *o = &positionInLastFrame->ToF_position[row][col];
+            o->x = g->x - transform[0];
+            o->y = g->y - transform[1];
+            o->z = g->z - transform[2];
+        }
+}
+
 int getAxis(int depth) { return depth % 3; }
 
 double euclideanDistance(Point p1, Point p2) {
@@ -336,6 +348,11 @@ static void select_nth(Point *p, size_t first, size_t last, size_t nth, int axis
         else
             last = store - 1;
     }
+}
+
+/* utils/kdtree.c:20-62 has external linkage in the reference: same in-place partial ordering */
+void nth_element(Point *points, size_t first, size_t last, size_t nth, int axis) {
+    select_nth(points, first, last, nth, axis);
 }
 
 static void print_subtree(Point *p, size_t n, int build_depth, int print_depth) {

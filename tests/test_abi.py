@@ -6,6 +6,7 @@ import importlib
 import os
 import re
 
+import numpy as np
 import pytest
 
 from oracle_lib import RefLib, ref_available
@@ -14,7 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHAPES = [(8, 8), (5, 33), (16, 1800), (64, 2048)]
 REF_SYMBOLS = ["convertToPointCloud", "printPointCloud", "init_slam", "slam_localization", "slam_mapping",
                "printKDTree", "buildKDTree", "freeKDTree", "nearestNeighborSearch", "extract_feature",
-               "flattenPoints", "compute_posdiff", "getRotationMatrix", "getAxis", "euclideanDistance"]
+               "flattenPoints", "compute_posdiff", "getRotationMatrix", "getAxis", "euclideanDistance",
+               "mapCoordinatesToLastFrame", "nth_element"]
 
 
 @pytest.fixture(scope="module")
@@ -82,3 +84,35 @@ def test_product_never_imports_the_oracle():
     # build.py may *link* the reference's main.o against the shim (a test artefact kept in oracle/_ref)
     bad = [b for b in bad if not b.endswith("build.py")]
     assert not bad, bad
+
+
+def test_shim_host_helpers_match_reference(built):
+    """nth_element and mapCoordinatesToLastFrame are plain host code in the shim: same results as the
+    reference's compiled functions (oracle/_ref), no GPU involved."""
+    from oracle_lib import ref_available
+    if not ref_available("8x8"):
+        pytest.skip("oracle/_ref not built")
+    S = C.CDLL(built.build.shim_path(8, 8))
+    R = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libnavref_8x8.so"))
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 7, 64, 501):
+        for axis in (0, 1, 2):
+            pts = np.round(rng.normal(0, 50, (n, 3)))          # rounded: plenty of equal keys
+            a, b = pts.copy(), pts.copy()
+            for L, arr in ((S, a), (R, b)):
+                L.nth_element.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int]
+                L.nth_element.restype = None
+                L.nth_element(arr.ctypes.data, 0, n - 1, n // 2, axis)
+            assert np.array_equal(a, b)
+    cloud = np.zeros(8 + 8 * 8 * 24, dtype=np.uint8)
+    pts = rng.normal(0, 1000, (8, 8, 3))
+    cloud[8:] = np.frombuffer(pts.tobytes(), dtype=np.uint8)
+    tr = np.array([12.5, -3.25, 100.0])
+    outs = []
+    for L in (S, R):
+        out = np.zeros_like(cloud)
+        L.mapCoordinatesToLastFrame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mapCoordinatesToLastFrame.restype = None
+        L.mapCoordinatesToLastFrame(cloud.ctypes.data, tr.ctypes.data, out.ctypes.data)
+        outs.append(out[8:].copy().view(np.float64))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0].reshape(8, 8, 3), pts - tr)
