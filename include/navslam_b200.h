@@ -130,11 +130,14 @@ int nav_slam_localization(nav_ctx *ctx, const nav_point *cloud, const nav_pos *p
 /* The same step with the fit driven by five sufficient statistics reduced on the device (N, sum r,
  * sum |r|^2 with r = ori - nearest): nothing but 40 bytes comes back and each of the 200
  * iterations is O(1).  Sums are formed in a different order than the reference's sequential loop, so
- * the pose agrees with nav_slam_localization to rounding (about 1e-9 relative), not bit for bit. */
+ * the pose agrees with nav_slam_localization to rounding (about 1e-9 relative), not bit for bit.  The sums
+ * are formed in a fixed order (deterministic).  cloud may be a frame queued by nav_slam_prefetch, or NULL
+ * for the oldest prefetched frame. */
 int nav_slam_localization_fast(nav_ctx *ctx, const nav_point *cloud, const nav_pos *pos_predict,
                                const nav_pos *pos_last, nav_pos *pos_out, double *error_out, size_t *n_corr_out);
 /* slam_mapping (src/slam.c:393): global_out = pose(cloud), per-row map for the next frame.
- * cloud == NULL reuses the cloud (and labels) of the preceding nav_slam_match/localization call. */
+ * cloud == NULL reuses the cloud (and labels) of the preceding nav_slam_match/localization call; with
+ * global_out == NULL as well the call only queues the map kernel and does not synchronise. */
 int nav_slam_mapping(nav_ctx *ctx, const nav_pos *pos, const nav_point *cloud, nav_point *global_out);
 /* one front-end frame with raw per-pixel outputs (SURVEY 8d "one frame of work"): labels, queries,
  * NN vs the previous frame, then mapping with pos_final.  nn_idx = flat pixel (row*cols+col) of the
@@ -162,6 +165,50 @@ int nav_frontend_frame_async(nav_ctx *ctx, const nav_point *cloud, const nav_pos
                              const nav_pos *pos_last, const nav_pos *pos_final, int *feature_out,
                              int32_t *nn_idx_out, double *nn_dist_out, nav_point *global_out);
 int nav_frontend_wait(nav_ctx *ctx);
+
+/* General form of the pipelined call.  Exactly one of cloud / distances is the input: `distances` is the L5
+ * depth matrix of utils/pointcloud.h:13-17 (int mm, rows x cols, n_seq == 1), converted on the device
+ * (utils/pointcloud.c:8) -- 4 B/pixel cross PCIe instead of 24.  Every output is optional.  mask_out returns
+ * the labels as bit masks, uint32 [n_seq][rows][ceil(cols/16)], bit i (i < 16) of word b = label of column
+ * 16*b + i: 32 KB instead of the 512 KB of feature_out at 64x2048.  cloud_out (depth input only) receives
+ * the converted lidar-frame cloud.  Adjacent host buffers feature_out | nn_idx_out | nn_dist_out (or
+ * nn_idx_out | nn_dist_out when feature_out is NULL) are filled by a single copy. */
+typedef struct {
+    const nav_point *cloud;
+    const int *distances;
+    nav_point *cloud_out;
+    int *feature_out;
+    uint32_t *mask_out;
+    int32_t *nn_idx_out;
+    double *nn_dist_out;
+    nav_point *global_out;
+} nav_frame_io;
+int nav_frontend_submit(nav_ctx *ctx, const nav_frame_io *io, const nav_pos *pos_predict,
+                        const nav_pos *pos_last, const nav_pos *pos_final);
+/* nav_frontend_frame_depth, pipelined (src/main.c:194-197,308: depth -> xyz -> SLAM step per frame) */
+int nav_frontend_frame_depth_async(nav_ctx *ctx, const int *distances, const nav_pos *pos_predict,
+                                   const nav_pos *pos_last, const nav_pos *pos_final, nav_point *cloud_out,
+                                   int *feature_out, int32_t *nn_idx_out, double *nn_dist_out, nav_point *global_out);
+
+/* Closed loop with pose feedback (src/main.c:300-318): localization(t) needs pose(t-1) and mapping(t) needs
+ * pose(t), but the upload of frame t+1 and its labels (src/slam.c:11, pose independent) need neither.
+ * nav_slam_prefetch queues both on a copy stream and returns at once; a later
+ * nav_slam_localization_fast(ctx, cloud, ...) with the same `cloud` pointer (or NULL = the oldest prefetched
+ * frame) finds the frame resident and labelled and only runs match + dedupe + statistics (2.5 KB come back).
+ * nav_slam_mapping(ctx, pos, NULL, NULL) then maps that frame without synchronising.  Up to two frames may
+ * be prefetched ahead.  The host buffer must be pinned and stay untouched until the localization call
+ * that consumes it returns.
+ *     nav_slam_prefetch(ctx, frame[1]);
+ *     for (t = 1; t < n; ++t) {
+ *         if (t + 1 < n) nav_slam_prefetch(ctx, frame[t + 1]);
+ *         nav_slam_localization_fast(ctx, frame[t], &predict, &last, &pose, &err, NULL);
+ *         nav_slam_mapping(ctx, &pose, NULL, NULL);
+ *     }
+ * Poses are identical to the same calls without prefetch. */
+int nav_slam_prefetch(nav_ctx *ctx, const nav_point *cloud);
+/* the same for L5 input: uploads the depth matrix and converts it on the device; consume it with
+ * nav_slam_localization_fast(ctx, NULL, ...) */
+int nav_slam_prefetch_depth(nav_ctx *ctx, const int *distances);
 
 /* ---- data formats either side of the path (host code) ----------------- */
 /* replaces L9_LidarProcessData (src/main.c:77-128): parses "frame,row,col,x,y,z,conf" records after one

@@ -109,6 +109,9 @@ struct nav_kdtree;
 int navslam_nn_batch(KDNode *root, const Point *targets, size_t n, int *index_out, double *dist_out,
                      Point *nearest_out);
 struct nav_ctx *navslam_context_of(SLAM_attr *attr);
+/* give the device context behind a SLAM_attr back (the reference has no teardown call; anything still
+ * held is released at exit) */
+void navslam_release(SLAM_attr *attr);
 struct nav_kdtree *navslam_tree_of(KDNode *root);
 
 #endif

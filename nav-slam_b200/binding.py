@@ -26,6 +26,12 @@ class NavFrameResults(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("labels", "nn_idx", "nn_dist", "global_", "map_mask")]
 
 
+class NavFrameIO(C.Structure):
+    """nav_frame_io of include/navslam_b200.h (pinned host pointers, any output may be None)."""
+    _fields_ = [(n, C.c_void_p) for n in ("cloud", "distances", "cloud_out", "feature_out", "mask_out",
+                                          "nn_idx_out", "nn_dist_out", "global_out")]
+
+
 class NavError(RuntimeError):
     pass
 
@@ -47,6 +53,7 @@ EXPORTS = [
     "nav_frontend_sequence_dev", "nav_slam_localization_fast", "nav_frontend_frame_depth",
     "nav_l9_csv_read", "nav_csv_header", "nav_csv_format_frame", "nav_csv_format_frame_gpu",
     "nav_csv_format_frame_dev", "nav_l5_json_read", "nav_imu_json_read",
+    "nav_frontend_submit", "nav_frontend_frame_depth_async", "nav_slam_prefetch", "nav_slam_prefetch_depth",
 ]
 
 
@@ -114,6 +121,12 @@ def load_library(build_if_missing: bool = True):
     L.nav_frontend_frame_async.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
                                            vp, vp, vp, vp]
     L.nav_frontend_wait.argtypes = [vp]
+    L.nav_frontend_submit.argtypes = [vp, C.POINTER(NavFrameIO), C.POINTER(NavPos), C.POINTER(NavPos),
+                                      C.POINTER(NavPos)]
+    L.nav_frontend_frame_depth_async.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
+                                                 vp, vp, vp, vp, vp]
+    L.nav_slam_prefetch.argtypes = [vp, vp]
+    L.nav_slam_prefetch_depth.argtypes = [vp, vp]
     L.nav_l9_csv_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_size_t, vp, vp, C.POINTER(C.c_size_t)]
     L.nav_csv_format_frame_gpu.argtypes = [vp, C.c_ulonglong, vp, vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), vp,
                                            C.c_size_t, C.POINTER(C.c_size_t)]
@@ -320,6 +333,29 @@ class Context:
         _check(self.L.nav_frontend_frame_async(self.h, cloud_ptr, _pos_array(pos_predict, n),
                                                _pos_array(pos_last, n), _pos_array(pos_final, n), feat_ptr,
                                                idx_ptr, dist_ptr, global_ptr), self.L)
+
+    def frontend_submit(self, pos_predict, pos_last, pos_final, **ptrs):
+        """nav_frontend_submit: keyword arguments are the fields of nav_frame_io (pinned host pointers as ints)."""
+        io = NavFrameIO(**ptrs)
+        n = self.n_seq
+        _check(self.L.nav_frontend_submit(self.h, C.byref(io), _pos_array(pos_predict, n), _pos_array(pos_last, n),
+                                          _pos_array(pos_final, n)), self.L)
+
+    def slam_prefetch(self, cloud_ptr=None, depth_ptr=None):
+        """nav_slam_prefetch / nav_slam_prefetch_depth with a pinned host pointer (int)."""
+        if depth_ptr is not None:
+            _check(self.L.nav_slam_prefetch_depth(self.h, depth_ptr), self.L)
+        else:
+            _check(self.L.nav_slam_prefetch(self.h, cloud_ptr), self.L)
+
+    def slam_localization_fast_ptr(self, cloud_ptr, pos_predict, pos_last):
+        """nav_slam_localization_fast on a raw host pointer (int) or None = the oldest prefetched frame."""
+        out = NavPos()
+        err = C.c_double(0)
+        n = C.c_size_t(0)
+        _check(self.L.nav_slam_localization_fast(self.h, cloud_ptr, _pos_array(pos_predict), _pos_array(pos_last),
+                                                 C.byref(out), C.byref(err), C.byref(n)), self.L)
+        return np.array([out.x, out.y, out.z, out.roll, out.pitch, out.yaw]), err.value, int(n.value)
 
     def frontend_wait(self):
         _check(self.L.nav_frontend_wait(self.h), self.L)

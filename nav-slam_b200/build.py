@@ -95,37 +95,10 @@ def build_shims(shapes=SHIM_SHAPES, force: bool = False):
     return out
 
 
-def link_reference_mains(shapes=SHIM_SHAPES):
-    """If oracle/_ref/obj holds the reference's main.c / ekf.c objects (compiled by
-    oracle/build_ref.sh from /root/reference), link them UNMODIFIED against the shim: the
-    reference's driver program running on the B200 library.  Test artefact, kept in oracle/_ref."""
-    objdir = os.path.join(ROOT, "oracle", "_ref", "obj")
-    cc = os.environ.get("CC") or shutil.which("gcc") or "gcc"
-    l9 = os.path.join(ROOT, "oracle", "l9_main.c")
-    out = []
-    for r, c in shapes:
-        shape = f"{r}x{c}"
-        main_o = os.path.join(objdir, f"main_{shape}.o")
-        nomain_o = os.path.join(objdir, f"main_nomain_{shape}.o")
-        ekf_o = os.path.join(objdir, f"ekf_{shape}.o")
-        so = shim_path(r, c)
-        if not (os.path.exists(main_o) and os.path.exists(so)):
-            continue
-        common = [f"-L{BUILD}", f"-lnavslam_shim_{shape}", "-lnavslam_b200",
-                  f"-Wl,-rpath,{BUILD}", "-lm", "-l:libjansson.so.4"]
-        exe = os.path.join(ROOT, "oracle", "_ref", f"navshim_main_{shape}")
-        subprocess.check_call([cc, main_o, ekf_o, *common, "-o", exe])
-        exe9 = os.path.join(ROOT, "oracle", "_ref", f"navshim_l9_{shape}")
-        subprocess.check_call([cc, "-O2", l9, nomain_o, ekf_o, *common, "-o", exe9])
-        out += [exe, exe9]
-    return out
-
-
 def build_all(verbose: bool = False, force: bool = False):
     lib = build_library(verbose=verbose, force=force)
     shims = build_shims(force=force)
-    mains = link_reference_mains()
-    return lib, shims, mains
+    return lib, shims
 
 
 if __name__ == "__main__":

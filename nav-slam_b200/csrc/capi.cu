@@ -88,13 +88,22 @@ struct Stager {
     size_t cap = 0, used = 0;
     std::vector<PendingOut> pending;
 
+    // cudaPointerGetAttributes costs about a microsecond; the pipelined entry points are called with the
+    // same few buffers frame after frame, so pointers already seen to be pinned are remembered
+    // (a buffer that stops being pinned would merely be copied through the driver's own staging)
     static bool is_pinned(const void *p) {
+        static thread_local const void *seen[16] = {};
+        static thread_local unsigned next = 0;
+        for (const void *s : seen)
+            if (s == p) return true;
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
             cudaGetLastError();
             return false;
         }
-        return at.type == cudaMemoryTypeHost;
+        if (at.type != cudaMemoryTypeHost) return false;
+        seen[next++ & 15u] = p;
+        return true;
     }
     // staging space lives for one API call; growing needs the stream idle
     unsigned char *take(size_t bytes, cudaStream_t stream) {
@@ -190,14 +199,34 @@ struct nav_ctx {
     Stager stage;
     bool have_map = false, cloud_resident = false;
     uint64_t launches = 0;
-    // pipelined host path (nav_frontend_frame_async): two slots, copy-in / copy-out streams
+    // pipelined host path (nav_frontend_submit / nav_frontend_frame_async): copy-in / copy-out streams and
+    // as many slots as there are map buffers -- the download of frame t reads the map built by frame t
+    // (global cloud, label masks) straight out of its ping-pong buffer, which frame t+2 overwrites; frame
+    // t+2 uses the same slot and waits for that download.
+    static constexpr int kSlots = 2;
     struct AsyncSlot {
-        double *d_cloud = nullptr, *d_nn_dist = nullptr, *d_global = nullptr;
-        int *d_labels = nullptr, *d_nn_idx = nullptr;
+        double *d_cloud = nullptr, *d_nn_dist = nullptr;
+        int *d_labels = nullptr, *d_nn_idx = nullptr, *d_depth = nullptr;
         cudaEvent_t in_done = nullptr, compute_done = nullptr, out_done = nullptr;
-    } slots[2];
+    } slots[kSlots];
     cudaStream_t s_in = nullptr, s_out = nullptr;
     uint64_t async_frames = 0;
+    bool async_synced = true;  // the context's own result buffers hold the last pipelined frame
+    // closed-loop prefetch (nav_slam_prefetch): the next frame is uploaded and labelled on the copy-in
+    // stream while the current one is matched and fitted
+    struct PreSlot {
+        double *d_cloud = nullptr;
+        int *d_labels = nullptr, *d_depth = nullptr;
+        cudaEvent_t ready = nullptr, released = nullptr;
+        const void *host_src = nullptr;  // identity of the prefetched frame
+        bool pending = false;
+    } pre[2];
+    int pre_next = 0;
+    // the frame the last localization call worked on (mapping with cloud == NULL maps this one)
+    const double *cur_cloud = nullptr;
+    int *cur_labels = nullptr;
+    double *d_row_stats = nullptr;  // [n_seq*rows][5] per-row sufficient statistics of the translation fit
+    double *h_row_stats = nullptr;  // pinned copy
     bool prof = false;
     ProfSlot prof_labels, prof_match, prof_map;
 };
@@ -279,11 +308,19 @@ extern "C" void nav_destroy(nav_ctx *c) {
     if (c->d_csv) cudaFree(c->d_csv);
     if (c->d_csv_scratch) cudaFree(c->d_csv_scratch);
     for (auto &sl : c->slots) {
-        for (void *p : {(void *)sl.d_cloud, (void *)sl.d_labels})  // the other outputs live inside d_labels
+        for (void *p : {(void *)sl.d_cloud, (void *)sl.d_labels, (void *)sl.d_depth})  // the other outputs live inside d_labels
             if (p) cudaFree(p);
         for (cudaEvent_t e : {sl.in_done, sl.compute_done, sl.out_done})
             if (e) cudaEventDestroy(e);
     }
+    for (auto &ps : c->pre) {
+        for (void *p : {(void *)ps.d_cloud, (void *)ps.d_labels, (void *)ps.d_depth})
+            if (p) cudaFree(p);
+        for (cudaEvent_t e : {ps.ready, ps.released})
+            if (e) cudaEventDestroy(e);
+    }
+    if (c->d_row_stats) cudaFree(c->d_row_stats);
+    if (c->h_row_stats) cudaFreeHost(c->h_row_stats);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     c->stage.release();
@@ -350,6 +387,7 @@ extern "C" nav_ctx *nav_create(int rows, int cols, int device, int n_seq) {
     ALLOC(c->map.mask, nr * c->map.n_chunks * 4);
     ALLOC(c->d_n_exact, 4);
     ALLOC(c->d_stats, (size_t)n_seq * 5 * 8);
+    ALLOC(c->d_row_stats, nr * 5 * 8);
     ALLOC(c->map.box, nr * c->map.n_chunks * 32);
     ALLOC(c->map.sbox, nr * c->map.n_super * 32);
     c->map_alt.n_chunks = c->map.n_chunks;
@@ -370,7 +408,8 @@ extern "C" nav_ctx *nav_create(int rows, int cols, int device, int n_seq) {
 #undef ALLOC
     cudaMemsetAsync(c->map.mask, 0, nr * c->map.n_chunks * 4, c->stream);
     cudaMemsetAsync(c->d_n_exact, 0, 4, c->stream);
-    if (cudaHostAlloc((void **)&c->h_small, 4096, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc((void **)&c->h_small, 4096, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&c->h_row_stats, nr * 5 * 8, cudaHostAllocDefault) != cudaSuccess) {
         fail("nav_create: pinned scratch allocation failed");
         nav_destroy(c);
         return nullptr;
@@ -470,28 +509,46 @@ static void run_labels(nav_ctx *c, const double *d_cloud, int *d_labels, double 
     c->launches++;
 }
 
+// a synchronous entry point that touches the maps must not overtake the downloads of pipelined frames
+// still reading them (nav_frontend_submit): order the context's stream behind those copies
+static void order_after_async(nav_ctx *c) {
+    if (!c->async_frames || c->async_synced) return;
+    for (auto &sl : c->slots)
+        if (sl.out_done) cudaStreamWaitEvent(c->stream, sl.out_done, 0);
+}
+
 // transform + label masks + boxes of the frame whose labels are in d_labels (a7 + a4/a5)
-static void run_map(nav_ctx *c, const double *d_cloud, const PoseBatch &poses) {
+static void run_map(nav_ctx *c, const double *d_cloud, const int *d_labels, const PoseBatch &poses) {
+    order_after_async(c);
     ProfScope ps(c, &c->prof_map);
-    launch_frame_map(d_cloud, c->d_labels, c->map, poses, c->n_seq, c->rows, c->cols, c->stream);
+    launch_frame_map(d_cloud, d_labels, c->map, poses, c->n_seq, c->rows, c->cols, c->stream);
     c->launches++;
     c->have_map = true;
 }
 
-// labels (a3, fused into the match kernel) + queries (a7) + exact per-row NN (a6) [+ dedupe (a8)]
-static void run_match(nav_ctx *c, const double *d_cloud, const PoseBatch &poses, bool dedupe) {
+// labels (a3: fused into the match kernel, or already in d_labels) + queries (a7) + exact per-row NN (a6),
+// then the per-row dedupe (a8) producing the correspondence list and/or the per-row fit statistics
+enum { kDedupeNone = 0, kDedupeCorr = 1, kDedupeStats = 2 };
+static void run_match(nav_ctx *c, const double *d_cloud, int *d_labels, bool fused_labels, const PoseBatch &poses,
+                      int dedupe) {
+    order_after_async(c);
     MatchOut out = {c->d_nn_idx, c->d_nn_dist, c->d_corr_rows, c->d_corr_row_count};
     {
         ProfScope ps(c, &c->prof_match);
-        launch_frame_match(d_cloud, c->d_labels, true, c->map, out, poses, c->n_seq, c->rows, c->cols,
+        launch_frame_match(d_cloud, d_labels, fused_labels, c->map, out, poses, c->n_seq, c->rows, c->cols,
                            c->d_n_exact, c->stream);
         c->launches++;
     }
-    if (dedupe) {
-        launch_dedupe(d_cloud, c->d_labels, c->map, out, poses, c->n_seq, c->rows, c->cols, c->stream);
+    if (dedupe & kDedupeCorr) {
+        launch_dedupe(d_cloud, d_labels, c->map, out, poses, c->n_seq, c->rows, c->cols, c->stream,
+                      (dedupe & kDedupeStats) ? c->d_row_stats : nullptr, true);
         launch_gather_corr(c->d_corr_rows, c->d_corr_row_count, c->d_corr, c->d_corr_total, c->n_seq, c->rows,
                            c->cols, c->stream);
         c->launches += 2;
+    } else if (dedupe & kDedupeStats) {
+        launch_dedupe(d_cloud, d_labels, c->map, out, poses, c->n_seq, c->rows, c->cols, c->stream, c->d_row_stats,
+                      false);
+        c->launches += 1;
     }
 }
 
@@ -611,8 +668,10 @@ extern "C" int nav_slam_init(nav_ctx *c, const nav_pos *pos, const nav_point *cl
     if (c->stage.reserve(c->ntot * 48 + 1024, c->stream)) return fail("nav_slam_init: staging");
     if (upload_cloud(c, cloud, "nav_slam_init")) return 1;
     run_labels(c, c->d_cloud, c->d_labels, nullptr, c->n_seq);
-    run_map(c, c->d_cloud, pose_batch(c, pos, nullptr));
+    run_map(c, c->d_cloud, c->d_labels, pose_batch(c, pos, nullptr));
     c->cloud_resident = true;
+    c->cur_cloud = c->d_cloud;
+    c->cur_labels = c->d_labels;
     if (global_out && c->stage.d2h(global_out, c->map.pts, c->ntot * 24, c->stream))
         return fail("nav_slam_init: D2H");
     return finish_call(c, "nav_slam_init");
@@ -622,7 +681,7 @@ extern "C" int nav_slam_init_dev(nav_ctx *c, const void *dev_cloud, const nav_po
     CTX_ENTER(c, "nav_slam_init_dev");
     if (!pos || !dev_cloud) return fail("nav_slam_init_dev: null argument");
     run_labels(c, (const double *)dev_cloud, c->d_labels, nullptr, c->n_seq);
-    run_map(c, (const double *)dev_cloud, pose_batch(c, pos, nullptr));
+    run_map(c, (const double *)dev_cloud, c->d_labels, pose_batch(c, pos, nullptr));
     c->cloud_resident = false;
     CU(cudaGetLastError());
     return 0;
@@ -637,8 +696,10 @@ extern "C" int nav_slam_match(nav_ctx *c, const nav_point *cloud, const nav_pos 
     if (c->stage.reserve(c->ntot * 24 + c->ntot * sizeof(nav_corr) + 1024, c->stream))
         return fail("nav_slam_match: staging");
     if (upload_cloud(c, cloud, "nav_slam_match")) return 1;
-    run_match(c, c->d_cloud, pose_batch(c, pos_predict, pos_last), true);
+    run_match(c, c->d_cloud, c->d_labels, true, pose_batch(c, pos_predict, pos_last), kDedupeCorr);
     c->cloud_resident = true;
+    c->cur_cloud = c->d_cloud;
+    c->cur_labels = c->d_labels;
     CU(cudaMemcpyAsync(c->h_small, c->d_corr_total, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     const size_t n = (size_t)c->h_small[0];
@@ -716,6 +777,63 @@ extern "C" int nav_slam_localization(nav_ctx *c, const nav_point *cloud, const n
     return 0;
 }
 
+// ---- closed loop with prefetch -------------------------------------------------------------------------
+// The reference's loop is serial in the pose (src/main.c:300-318: localization(t) needs pose(t-1), mapping(t)
+// needs pose(t)), but uploading frame t+1 and labelling it (a3 is pose independent) need neither.
+// nav_slam_prefetch queues both on the copy-in stream, so they run under frame t's match, download and
+// host fit; nav_slam_localization_fast then finds the frame resident and labelled.
+static int pre_setup(nav_ctx *c) {
+    if (c->pre[0].d_cloud) return 0;
+    if (!c->s_in) CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    for (auto &ps : c->pre) {
+        CU(cudaMalloc((void **)&ps.d_cloud, c->ntot * 24));
+        CU(cudaMalloc((void **)&ps.d_labels, c->ntot * 4));
+        CU(cudaEventCreateWithFlags(&ps.ready, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ps.released, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+static int prefetch_common(nav_ctx *c, const char *name, const nav_point *cloud, const int *distances) {
+    const void *src = cloud ? (const void *)cloud : (const void *)distances;
+    if (!src) return fail("%s: null argument", name);
+    if (distances && c->n_seq != 1) return fail("%s: depth input needs n_seq == 1", name);
+    if (!Stager::is_pinned(src)) return fail("%s: the host buffer must be pinned (nav_host_alloc / cudaHostRegister)", name);
+    if (pre_setup(c)) return 1;
+    nav_ctx::PreSlot &ps = c->pre[c->pre_next];
+    if (ps.pending) return fail("%s: two prefetched frames are already waiting for nav_slam_localization_fast", name);
+    // the slot's buffers were last used by the frame before the current one: its map kernel is the last
+    // reader and is already queued on the context's stream
+    CU(cudaEventRecord(ps.released, c->stream));
+    CU(cudaStreamWaitEvent(c->s_in, ps.released, 0));
+    if (distances) {
+        if (!ps.d_depth) CU(cudaMalloc((void **)&ps.d_depth, c->npx * 4));
+        CU(cudaMemcpyAsync(ps.d_depth, distances, c->npx * 4, cudaMemcpyHostToDevice, c->s_in));
+        launch_convert(ps.d_depth, c->d_tan_col, c->d_tan_row, ps.d_cloud, c->rows, c->cols, c->sm_count, c->s_in);
+        c->launches++;
+    } else {
+        CU(cudaMemcpyAsync(ps.d_cloud, cloud, c->ntot * 24, cudaMemcpyHostToDevice, c->s_in));
+    }
+    launch_labels(ps.d_cloud, ps.d_labels, nullptr, (long long)c->n_seq * c->rows, c->cols, c->sm_count, c->d_n_exact,
+                  c->s_in);
+    c->launches++;
+    CU(cudaEventRecord(ps.ready, c->s_in));
+    ps.host_src = src;
+    ps.pending = true;
+    c->pre_next ^= 1;
+    return 0;
+}
+
+extern "C" int nav_slam_prefetch(nav_ctx *c, const nav_point *cloud) {
+    CTX_ENTER(c, "nav_slam_prefetch");
+    return prefetch_common(c, "nav_slam_prefetch", cloud, nullptr);
+}
+
+extern "C" int nav_slam_prefetch_depth(nav_ctx *c, const int *distances) {
+    CTX_ENTER(c, "nav_slam_prefetch_depth");
+    return prefetch_common(c, "nav_slam_prefetch_depth", nullptr, distances);
+}
+
 // slam_localization with the fit driven by five sufficient statistics reduced on the device
 // (SURVEY 8f #2): no correspondence list crosses PCIe and the 200 iterations are O(1) each.
 // Same update rule as src/slam.c:341-370; sums are formed in a different order than the
@@ -724,19 +842,43 @@ extern "C" int nav_slam_localization_fast(nav_ctx *c, const nav_point *cloud, co
                                           const nav_pos *pos_last, nav_pos *pos_out, double *error_out,
                                           size_t *n_corr_out) {
     CTX_ENTER(c, "nav_slam_localization_fast");
-    if (!cloud || !pos_predict || !pos_last || !pos_out) return fail("nav_slam_localization_fast: null argument");
+    if (!pos_predict || !pos_last || !pos_out) return fail("nav_slam_localization_fast: null argument");
     if (c->n_seq != 1) return fail("nav_slam_localization_fast: needs n_seq == 1");
     if (!c->have_map) return fail("nav_slam_localization_fast: call nav_slam_init first");
-    if (c->stage.reserve(c->ntot * 24 + 1024, c->stream)) return fail("nav_slam_localization_fast: staging");
-    if (upload_cloud(c, cloud, "nav_slam_localization_fast")) return 1;
-    run_match(c, c->d_cloud, pose_batch(c, pos_predict, pos_last), true);
-    launch_corr_stats(c->d_corr, c->d_corr_total, c->d_stats, 1, c->rows, c->cols, c->sm_count, c->stream);
-    c->launches++;
+    // a prefetched frame?  (cloud == NULL: the oldest one waiting; otherwise the one uploaded from `cloud`)
+    nav_ctx::PreSlot *ps = nullptr;
+    for (int k = 0; k < 2 && !ps; ++k) {
+        nav_ctx::PreSlot &cand = c->pre[(c->pre_next + k) & 1];  // pre_next is the older of two pending slots
+        if (cand.pending && (!cloud || cand.host_src == (const void *)cloud)) ps = &cand;
+    }
+    if (!ps && !cloud) return fail("nav_slam_localization_fast: cloud == NULL but no frame has been prefetched");
+    const PoseBatch poses = pose_batch(c, pos_predict, pos_last);
+    if (ps) {
+        CU(cudaStreamWaitEvent(c->stream, ps->ready, 0));
+        run_match(c, ps->d_cloud, ps->d_labels, false, poses, kDedupeStats);
+        ps->pending = false;
+        c->cur_cloud = ps->d_cloud;
+        c->cur_labels = ps->d_labels;
+    } else {
+        if (c->stage.reserve(c->ntot * 24 + 1024, c->stream)) return fail("nav_slam_localization_fast: staging");
+        if (upload_cloud(c, cloud, "nav_slam_localization_fast")) return 1;
+        run_match(c, c->d_cloud, c->d_labels, true, poses, kDedupeStats);
+        c->cur_cloud = c->d_cloud;
+        c->cur_labels = c->d_labels;
+    }
     c->cloud_resident = true;
-    double *h = (double *)c->h_small;
-    CU(cudaMemcpyAsync(h, c->d_stats, 40, cudaMemcpyDeviceToHost, c->stream));
+    const size_t stats_bytes = (size_t)c->rows * 5 * 8;
+    CU(cudaMemcpyAsync(c->h_row_stats, c->d_row_stats, stats_bytes, cudaMemcpyDeviceToHost, c->stream));
     if (finish_call(c, "nav_slam_localization_fast")) return 1;
-    const double N = h[0], S[3] = {h[1], h[2], h[3]}, Q = h[4];
+    double N = 0, S[3] = {0, 0, 0}, Q = 0;
+    for (int r = 0; r < c->rows; ++r) {  // rows in order: the sums are the same bits on every run
+        const double *h = c->h_row_stats + (size_t)r * 5;
+        N += h[0];
+        S[0] += h[1];
+        S[1] += h[2];
+        S[2] += h[3];
+        Q += h[4];
+    }
     double t[6] = {pos_predict->x - pos_last->x,       pos_predict->y - pos_last->y,
                    pos_predict->z - pos_last->z,       pos_predict->roll - pos_last->roll,
                    pos_predict->pitch - pos_last->pitch, pos_predict->yaw - pos_last->yaw};
@@ -747,11 +889,12 @@ extern "C" int nav_slam_localization_fast(nav_ctx *c, const nav_point *cloud, co
         if (N == 0) total = 0;
         if (fabs(total - prev) < tol) break;
         prev = total;
+        const double c1 = 1 - pow(b1, iter + 1), c2 = 1 - pow(b2, iter + 1);
         for (int j = 0; j < 3; ++j) {
             const double g = N > 0 ? -(S[j] - N * t[j]) / N : 0.0;
             m[j] = b1 * m[j] + (1 - b1) * g;
             v[j] = b2 * v[j] + (1 - b2) * g * g;
-            const double mh = m[j] / (1 - pow(b1, iter + 1)), vh = v[j] / (1 - pow(b2, iter + 1));
+            const double mh = m[j] / c1, vh = v[j] / c2;
             t[j] -= lr * mh / (sqrt(vh) + eps);
         }
     }
@@ -774,10 +917,16 @@ extern "C" int nav_slam_mapping(nav_ctx *c, const nav_pos *pos, const nav_point 
         if (upload_cloud(c, cloud, "nav_slam_mapping")) return 1;
         run_labels(c, c->d_cloud, c->d_labels, nullptr, c->n_seq);
         c->cloud_resident = true;
-    } else if (!c->cloud_resident) {
+        c->cur_cloud = c->d_cloud;
+        c->cur_labels = c->d_labels;
+    } else if (!c->cloud_resident || !c->cur_cloud) {
         return fail("nav_slam_mapping: cloud == NULL but no cloud is resident from a preceding match");
     }
-    run_map(c, c->d_cloud, pose_batch(c, pos, nullptr));
+    run_map(c, c->cur_cloud, c->cur_labels, pose_batch(c, pos, nullptr));
+    if (!cloud && !global_out) {  // nothing to wait for: the map kernel is queued, errors surface at the next call
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (global_out && c->stage.d2h(global_out, c->map.pts, c->ntot * 24, c->stream))
         return fail("nav_slam_mapping: D2H");
     return finish_call(c, "nav_slam_mapping");
@@ -791,8 +940,11 @@ extern "C" int nav_frontend_frame(nav_ctx *c, const nav_point *cloud, const nav_
     if (!c->have_map) return fail("nav_frontend_frame: call nav_slam_init first");
     if (c->stage.reserve(c->ntot * (24 + 24 + 4 + 4 + 8) + 4096, c->stream)) return fail("nav_frontend_frame: staging");
     if (upload_cloud(c, cloud, "nav_frontend_frame")) return 1;
+    order_after_async(c);
     run_frame_fused(c, c->d_cloud, c->d_labels, c->d_nn_idx, c->d_nn_dist, pos_predict, pos_last, pos_final);
     c->cloud_resident = true;
+    c->cur_cloud = c->d_cloud;
+    c->cur_labels = c->d_labels;
     if (feature_out && c->stage.d2h(feature_out, c->d_labels, c->ntot * 4, c->stream)) return fail("nav_frontend_frame: D2H");
     if (nn_idx_out && c->stage.d2h(nn_idx_out, c->d_nn_idx, c->ntot * 4, c->stream)) return fail("nav_frontend_frame: D2H");
     if (nn_dist_out && c->stage.d2h(nn_dist_out, c->d_nn_dist, c->ntot * 8, c->stream)) return fail("nav_frontend_frame: D2H");
@@ -815,8 +967,11 @@ extern "C" int nav_frontend_frame_depth(nav_ctx *c, const int *distances, const 
     if (c->stage.h2d(c->d_dist, distances, c->npx * 4, c->stream)) return fail("nav_frontend_frame_depth: H2D");
     launch_convert(c->d_dist, c->d_tan_col, c->d_tan_row, c->d_cloud, c->rows, c->cols, c->sm_count, c->stream);
     c->launches++;
+    order_after_async(c);
     run_frame_fused(c, c->d_cloud, c->d_labels, c->d_nn_idx, c->d_nn_dist, pos_predict, pos_last, pos_final);
     c->cloud_resident = true;
+    c->cur_cloud = c->d_cloud;
+    c->cur_labels = c->d_labels;
     if (cloud_out && c->stage.d2h(cloud_out, c->d_cloud, c->ntot * 24, c->stream)) return fail("nav_frontend_frame_depth: D2H");
     if (feature_out && c->stage.d2h(feature_out, c->d_labels, c->ntot * 4, c->stream)) return fail("nav_frontend_frame_depth: D2H");
     if (nn_idx_out && c->stage.d2h(nn_idx_out, c->d_nn_idx, c->ntot * 4, c->stream)) return fail("nav_frontend_frame_depth: D2H");
@@ -954,19 +1109,18 @@ extern "C" int nav_csv_format_frame_gpu(nav_ctx *c, unsigned long long timestamp
 // Same work as nav_frontend_frame, but nothing blocks: frame t's upload (copy-in stream), frame
 // t-1's kernels (context stream) and frame t-2's downloads (copy-out stream) overlap, with two
 // device slots for the per-frame buffers.  All host pointers must be pinned.  Outputs of frame t
-// are valid after nav_frontend_wait() (or after two further async calls).
+// are valid after nav_frontend_wait() (or after two further submissions).
 static int async_setup(nav_ctx *c) {
     if (c->s_in) return 0;
     CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
     for (auto &sl : c->slots) {
         CU(cudaMalloc((void **)&sl.d_cloud, c->ntot * 24));
-        // the four outputs of a slot are one allocation [labels | nn_idx | nn_dist | global], so that a
-        // caller whose host buffers are laid out the same way gets them with a single copy
-        CU(cudaMalloc((void **)&sl.d_labels, c->ntot * 40));
+        // labels, NN index and NN distance of a slot are one allocation [labels | nn_idx | nn_dist], so
+        // that a caller whose host buffers are laid out the same way gets them with a single copy
+        CU(cudaMalloc((void **)&sl.d_labels, c->ntot * 16));
         sl.d_nn_idx = sl.d_labels + c->ntot;
         sl.d_nn_dist = (double *)(sl.d_nn_idx + c->ntot);
-        sl.d_global = sl.d_nn_dist + c->ntot;
         CU(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
@@ -974,52 +1128,95 @@ static int async_setup(nav_ctx *c) {
     return 0;
 }
 
-extern "C" int nav_frontend_frame_async(nav_ctx *c, const nav_point *cloud, const nav_pos *pos_predict,
-                                        const nav_pos *pos_last, const nav_pos *pos_final, int *feature_out,
-                                        int32_t *nn_idx_out, double *nn_dist_out, nav_point *global_out) {
-    CTX_ENTER(c, "nav_frontend_frame_async");
-    if (!cloud || !pos_predict || !pos_last || !pos_final) return fail("nav_frontend_frame_async: null argument");
-    if (!c->have_map) return fail("nav_frontend_frame_async: call nav_slam_init first");
+extern "C" int nav_frontend_submit(nav_ctx *c, const nav_frame_io *io, const nav_pos *pos_predict,
+                                   const nav_pos *pos_last, const nav_pos *pos_final) {
+    CTX_ENTER(c, "nav_frontend_submit");
+    if (!io || !pos_predict || !pos_last || !pos_final) return fail("nav_frontend_submit: null argument");
+    if (!io->cloud == !io->distances) return fail("nav_frontend_submit: give exactly one of cloud and distances");
+    if (io->distances && c->n_seq != 1) return fail("nav_frontend_submit: depth input needs n_seq == 1");
+    if (io->cloud_out && !io->distances) return fail("nav_frontend_submit: cloud_out is the converted depth matrix; there is none");
+    if (!c->have_map) return fail("nav_frontend_submit: call nav_slam_init first");
     if (async_setup(c)) return 1;
-    const void *hp[] = {cloud, feature_out, nn_idx_out, nn_dist_out, global_out};
+    const void *hp[] = {io->cloud, io->distances, io->cloud_out, io->feature_out, io->mask_out,
+                        io->nn_idx_out, io->nn_dist_out, io->global_out};
     for (const void *p : hp)
         if (p && !Stager::is_pinned(p))
-            return fail("nav_frontend_frame_async: host buffers must be pinned (nav_host_alloc / cudaHostRegister)");
-    nav_ctx::AsyncSlot &sl = c->slots[c->async_frames & 1];
-    const bool reused = c->async_frames >= 2;
+            return fail("nav_frontend_submit: host buffers must be pinned (nav_host_alloc / cudaHostRegister)");
+    static_assert(nav_ctx::kSlots == 2, "slots pair up with the two map buffers (see nav_ctx)");
+    nav_ctx::AsyncSlot &sl = c->slots[c->async_frames % nav_ctx::kSlots];
+    const bool reused = c->async_frames >= (uint64_t)nav_ctx::kSlots;
     // copy-in: the slot's cloud was last read by the kernels of frame t-2
     if (reused) CU(cudaStreamWaitEvent(c->s_in, sl.compute_done, 0));
-    CU(cudaMemcpyAsync(sl.d_cloud, cloud, c->ntot * 24, cudaMemcpyHostToDevice, c->s_in));
+    if (io->distances) {
+        if (!sl.d_depth) CU(cudaMalloc((void **)&sl.d_depth, c->npx * 4));
+        CU(cudaMemcpyAsync(sl.d_depth, io->distances, c->npx * 4, cudaMemcpyHostToDevice, c->s_in));
+    } else {
+        CU(cudaMemcpyAsync(sl.d_cloud, io->cloud, c->ntot * 24, cudaMemcpyHostToDevice, c->s_in));
+    }
     CU(cudaEventRecord(sl.in_done, c->s_in));
     // kernels: need the upload, and the slot's output buffers released by the downloads of frame t-2
     CU(cudaStreamWaitEvent(c->stream, sl.in_done, 0));
     if (reused) CU(cudaStreamWaitEvent(c->stream, sl.out_done, 0));
+    if (io->distances) {  // a2 on the device: 4 B/pixel crossed PCIe instead of 24
+        launch_convert(sl.d_depth, c->d_tan_col, c->d_tan_row, sl.d_cloud, c->rows, c->cols, c->sm_count, c->stream);
+        c->launches++;
+    }
     run_frame_fused(c, sl.d_cloud, sl.d_labels, sl.d_nn_idx, sl.d_nn_dist, pos_predict, pos_last, pos_final);
-    // the mapped cloud is persistent state (the next frame searches it): hand the copy-out stream a
-    // snapshot that sits next to the other outputs of the slot
-    if (global_out) CU(cudaMemcpyAsync(sl.d_global, c->map.pts, c->ntot * 24, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaEventRecord(sl.compute_done, c->stream));
     c->cloud_resident = false;
-    // copy-out
+    c->async_synced = false;
+    // copy-out.  The mapped cloud and the label masks are persistent state (the next frame searches them):
+    // they are read straight out of the map buffer this frame built, which stays untouched until the
+    // frame after next -- and that frame waits for this slot's downloads (out_done) first.
     CU(cudaStreamWaitEvent(c->s_out, sl.compute_done, 0));
-    const bool packed = feature_out && nn_idx_out == feature_out + c->ntot &&
-                        (void *)nn_dist_out == (void *)(nn_idx_out + c->ntot) &&
-                        (void *)global_out == (void *)(nn_dist_out + c->ntot);
-    const bool packed3 = !global_out && feature_out && nn_idx_out == feature_out + c->ntot &&
-                         (void *)nn_dist_out == (void *)(nn_idx_out + c->ntot);
-    if (packed) {
-        CU(cudaMemcpyAsync(feature_out, sl.d_labels, c->ntot * 40, cudaMemcpyDeviceToHost, c->s_out));
-    } else if (packed3) {  // labels | idx | dist adjacent, the mapped cloud stays in HBM
-        CU(cudaMemcpyAsync(feature_out, sl.d_labels, c->ntot * 16, cudaMemcpyDeviceToHost, c->s_out));
+    int *f = io->feature_out;
+    int32_t *ni = io->nn_idx_out;
+    double *nd = io->nn_dist_out;
+    if (f && ni == f + c->ntot && (void *)nd == (void *)(ni + c->ntot)) {  // labels | idx | dist adjacent: one copy
+        CU(cudaMemcpyAsync(f, sl.d_labels, c->ntot * 16, cudaMemcpyDeviceToHost, c->s_out));
+    } else if (!f && ni && (void *)nd == (void *)(ni + c->ntot)) {          // idx | dist adjacent
+        CU(cudaMemcpyAsync(ni, sl.d_nn_idx, c->ntot * 12, cudaMemcpyDeviceToHost, c->s_out));
     } else {
-        if (feature_out) CU(cudaMemcpyAsync(feature_out, sl.d_labels, c->ntot * 4, cudaMemcpyDeviceToHost, c->s_out));
-        if (nn_idx_out) CU(cudaMemcpyAsync(nn_idx_out, sl.d_nn_idx, c->ntot * 4, cudaMemcpyDeviceToHost, c->s_out));
-        if (nn_dist_out) CU(cudaMemcpyAsync(nn_dist_out, sl.d_nn_dist, c->ntot * 8, cudaMemcpyDeviceToHost, c->s_out));
-        if (global_out) CU(cudaMemcpyAsync(global_out, sl.d_global, c->ntot * 24, cudaMemcpyDeviceToHost, c->s_out));
+        if (f) CU(cudaMemcpyAsync(f, sl.d_labels, c->ntot * 4, cudaMemcpyDeviceToHost, c->s_out));
+        if (ni) CU(cudaMemcpyAsync(ni, sl.d_nn_idx, c->ntot * 4, cudaMemcpyDeviceToHost, c->s_out));
+        if (nd) CU(cudaMemcpyAsync(nd, sl.d_nn_dist, c->ntot * 8, cudaMemcpyDeviceToHost, c->s_out));
     }
+    if (io->mask_out)
+        CU(cudaMemcpyAsync(io->mask_out, c->map.mask, (size_t)c->n_seq * c->rows * c->map.n_chunks * 4,
+                           cudaMemcpyDeviceToHost, c->s_out));
+    if (io->global_out) CU(cudaMemcpyAsync(io->global_out, c->map.pts, c->ntot * 24, cudaMemcpyDeviceToHost, c->s_out));
+    if (io->cloud_out) CU(cudaMemcpyAsync(io->cloud_out, sl.d_cloud, c->ntot * 24, cudaMemcpyDeviceToHost, c->s_out));
     CU(cudaEventRecord(sl.out_done, c->s_out));
     c->async_frames++;
     return 0;
+}
+
+extern "C" int nav_frontend_frame_async(nav_ctx *c, const nav_point *cloud, const nav_pos *pos_predict,
+                                        const nav_pos *pos_last, const nav_pos *pos_final, int *feature_out,
+                                        int32_t *nn_idx_out, double *nn_dist_out, nav_point *global_out) {
+    if (!cloud) return fail("nav_frontend_frame_async: null argument");
+    nav_frame_io io = {};
+    io.cloud = cloud;
+    io.feature_out = feature_out;
+    io.nn_idx_out = nn_idx_out;
+    io.nn_dist_out = nn_dist_out;
+    io.global_out = global_out;
+    return nav_frontend_submit(c, &io, pos_predict, pos_last, pos_final);
+}
+
+extern "C" int nav_frontend_frame_depth_async(nav_ctx *c, const int *distances, const nav_pos *pos_predict,
+                                              const nav_pos *pos_last, const nav_pos *pos_final, nav_point *cloud_out,
+                                              int *feature_out, int32_t *nn_idx_out, double *nn_dist_out,
+                                              nav_point *global_out) {
+    if (!distances) return fail("nav_frontend_frame_depth_async: null argument");
+    nav_frame_io io = {};
+    io.distances = distances;
+    io.cloud_out = cloud_out;
+    io.feature_out = feature_out;
+    io.nn_idx_out = nn_idx_out;
+    io.nn_dist_out = nn_dist_out;
+    io.global_out = global_out;
+    return nav_frontend_submit(c, &io, pos_predict, pos_last, pos_final);
 }
 
 extern "C" int nav_frontend_wait(nav_ctx *c) {
@@ -1027,11 +1224,15 @@ extern "C" int nav_frontend_wait(nav_ctx *c) {
     CU(cudaStreamSynchronize(c->stream));
     if (c->s_out) CU(cudaStreamSynchronize(c->s_out));
     if (c->s_in) CU(cudaStreamSynchronize(c->s_in));
-    // the synchronous entry points read labels from the context's own buffer: bring it up to date
-    if (c->async_frames) {
-        nav_ctx::AsyncSlot &sl = c->slots[(c->async_frames - 1) & 1];
+    // the synchronous entry points and nav_frame_results_dev read labels / nn_idx / nn_dist from the
+    // context's own buffers: bring all three up to date with the last pipelined frame
+    if (c->async_frames && !c->async_synced) {
+        nav_ctx::AsyncSlot &sl = c->slots[(c->async_frames - 1) % nav_ctx::kSlots];
         CU(cudaMemcpyAsync(c->d_labels, sl.d_labels, c->ntot * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_nn_idx, sl.d_nn_idx, c->ntot * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_nn_dist, sl.d_nn_dist, c->ntot * 8, cudaMemcpyDeviceToDevice, c->stream));
         CU(cudaStreamSynchronize(c->stream));
+        c->async_synced = true;
     }
     return 0;
 }
@@ -1050,6 +1251,7 @@ extern "C" int nav_frontend_frame_dev(nav_ctx *c, const void *dev_cloud, const n
     CTX_ENTER(c, "nav_frontend_frame_dev");
     if (!dev_cloud || !pos_predict || !pos_last || !pos_final) return fail("nav_frontend_frame_dev: null argument");
     if (!c->have_map) return fail("nav_frontend_frame_dev: call nav_slam_init_dev first");
+    order_after_async(c);
     run_frame_fused(c, (const double *)dev_cloud, c->d_labels, c->d_nn_idx, c->d_nn_dist, pos_predict, pos_last,
                     pos_final);
     c->cloud_resident = false;
@@ -1064,6 +1266,7 @@ extern "C" int nav_frontend_sequence_dev(nav_ctx *c, const void *dev_frames, siz
     if (!dev_frames || !pos_predict || !pos_last || !pos_final) return fail("nav_frontend_sequence_dev: null argument");
     if (!c->have_map) return fail("nav_frontend_sequence_dev: call nav_slam_init_dev first");
     const double *base = (const double *)dev_frames;
+    order_after_async(c);
     for (size_t f = 0; f < n_frames; ++f) {
         const double *cl = base + f * c->ntot * 3;
         const size_t o = f * (size_t)c->n_seq;

@@ -42,8 +42,11 @@ void launch_frame_match(const double *cloud, int *labels, bool fused_labels, con
                         const MatchOut &out, const PoseBatch &poses, int n_seq, int rows, int cols,
                         unsigned *n_exact, cudaStream_t stream, const RowMap *map_next = nullptr,
                         const PoseBatch *final_poses = nullptr, bool pdl = false);
+// row_stats (optional): [n_seq*rows][5] per-row {n, sum r (3), sum |r|^2} of the deduped correspondences;
+// write_corr = false skips the correspondence entries themselves
 void launch_dedupe(const double *cloud, const int *labels, const RowMap &map, const MatchOut &out,
-                   const PoseBatch &poses, int n_seq, int rows, int cols, cudaStream_t stream);
+                   const PoseBatch &poses, int n_seq, int rows, int cols, cudaStream_t stream,
+                   double *row_stats = nullptr, bool write_corr = true);
 void launch_gather_corr(const nav_corr *corr_rows, const int *corr_row_count, nav_corr *corr_out,
                         int *corr_total, int n_seq, int rows, int cols, cudaStream_t stream);
 void launch_corr_stats(const nav_corr *corr, const int *corr_total, double *stats_out, int n_seq, int rows, int cols,

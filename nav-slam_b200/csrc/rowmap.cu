@@ -490,11 +490,19 @@ constexpr int kRowThreads = 512;
 // per-row dedupe, src/slam.c:247-283: one entry per matched map point; the query with the smallest
 // distance wins (earliest column on equal distance, strict '>' at slam.c:264); entries in order of
 // the first query that matched the point.  One CTA per (sequence,row); dynamic smem = 16 B * cols.
+// row_stats != null: additionally reduce the sufficient statistics of the translation fit over the row's
+// entries (r = ori - nearest): row_stats[rid][0..4] = {n, sum rx, sum ry, sum rz, sum |r|^2},
+// summed in a fixed order (thread-strided, then a shuffle tree, then warp by warp) -- deterministic, and
+// the host adds the rows in order.  write_corr == 0 skips the 56-byte entries (the statistics are all
+// the caller wants).
 __global__ void __launch_bounds__(kRowThreads)
 k_dedupe_rows(const double *__restrict__ cloud, const int *__restrict__ labels, RowMap map, MatchOut out,
-              const __grid_constant__ PoseBatch poses, int rows, int cols) {
+              const __grid_constant__ PoseBatch poses, int rows, int cols, double *__restrict__ row_stats,
+              int write_corr) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ int s_warp[65];
+    __shared__ double s_red[kRowThreads / 32][4];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     unsigned long long *s_best = (unsigned long long *)s_raw;
     int *s_first = (int *)(s_best + cols);
     int *s_win = s_first + cols;
@@ -549,11 +557,35 @@ k_dedupe_rows(const double *__restrict__ cloud, const int *__restrict__ labels, 
             e.nearest.y = np[1];
             e.nearest.z = np[2];
             e.distance = __longlong_as_double((long long)s_best[key]);
-            rows_out[pos] = e;
+            if (write_corr) rows_out[pos] = e;
+            if (row_stats) {
+                const double rx = dsub(ori.x, np[0]), ry = dsub(ori.y, np[1]), rz = dsub(ori.z, np[2]);
+                acc[0] = dadd(acc[0], rx);
+                acc[1] = dadd(acc[1], ry);
+                acc[2] = dadd(acc[2], rz);
+                acc[3] = dadd(acc[3], dsq3(rx, ry, rz));
+            }
         }
         n_out += total;
     }
     if (threadIdx.x == 0) out.corr_row_count[rid] = n_out;
+    if (row_stats) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) acc[k] = dadd(acc[k], __shfl_xor_sync(kFull, acc[k], d));
+        if (lane == 0)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s_red[warp][k] = acc[k];
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double t = 0.0;
+            for (int w = 0; w < kRowThreads / 32; ++w) t = dadd(t, s_red[w][threadIdx.x]);
+            row_stats[(long long)rid * 5 + 1 + threadIdx.x] = t;
+        }
+        if (threadIdx.x == 0) row_stats[(long long)rid * 5] = (double)n_out;
+    }
 }
 
 size_t dedupe_smem_bytes(int cols) { return (size_t)cols * 16; }
@@ -570,9 +602,10 @@ int configure_row_kernels(int cols) {
 }
 
 void launch_dedupe(const double *cloud, const int *labels, const RowMap &map, const MatchOut &out,
-                   const PoseBatch &poses, int n_seq, int rows, int cols, cudaStream_t stream) {
-    k_dedupe_rows<<<n_seq * rows, kRowThreads, dedupe_smem_bytes(cols), stream>>>(cloud, labels, map, out, poses,
-                                                                               rows, cols);
+                   const PoseBatch &poses, int n_seq, int rows, int cols, cudaStream_t stream, double *row_stats,
+                   bool write_corr) {
+    k_dedupe_rows<<<n_seq * rows, kRowThreads, dedupe_smem_bytes(cols), stream>>>(
+        cloud, labels, map, out, poses, rows, cols, row_stats, write_corr ? 1 : 0);
 }
 
 // rows of one sequence back to back: corr_out[seq][offset(row) + i]

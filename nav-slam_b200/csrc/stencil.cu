@@ -44,7 +44,9 @@ k_labels(const double *__restrict__ cloud, int *__restrict__ labels, long long n
 // whose taps never leave their row, and border columns get label 0.
 //   * loads: cp.async.bulk (TMA, 1-D) of the 5 856-byte tile into a 4-stage shared-memory ring; one
 //     elected thread issues the copy for tile k+3 while the CTA works on tile k.  Every tile starts
-//     at a multiple of 48 bytes, so the 16-byte alignment rule holds for any shape.
+//     at a multiple of 48 bytes, so the 16-byte alignment rule holds for the start of any tile; the
+//     size rule (a multiple of 16 bytes) fails only for the last tile of an odd-sized batch, whose
+//     final 8 bytes are stored by the producer thread itself.
 //   * full/empty mbarriers instead of __syncthreads: warps never wait for each other, only for data.
 //   * each warp owns 30 output points: its 32 lanes compute the forward distances of 32 consecutive
 //     points (fp64 differences -> fp32) and exchange them with two shuffles; lanes 2..31 then decide
@@ -130,8 +132,15 @@ k_labels_tma(const double *__restrict__ cloud, int *__restrict__ labels, unsigne
             const long long lo = g0 < 0 ? 0 : g0;
             const long long hi = g0 + kTileIn > (long long)n_pts ? (long long)n_pts : g0 + kTileIn;
             const unsigned bytes = (unsigned)(hi - lo) * 24u;
-            mbar_expect_tx(&s_full[p_stage], bytes);
-            bulk_g2s(&s_pts[p_stage][(int)(lo - g0) * 3], cloud + lo * 3, bytes, &s_full[p_stage]);
+            // bulk copies move multiples of 16 bytes.  Every tile starts at a multiple of 48 bytes and holds
+            // an even number of points, except the last tile of a batch with an odd number of points: its
+            // size is 8 mod 16.  The trailing double (z of the very last point, a tap of column cols-3) is
+            // then stored by hand; this thread's arrive below publishes it together with the copy.
+            const unsigned bulk = bytes & ~15u;
+            double *dst = &s_pts[p_stage][(int)(lo - g0) * 3];
+            if (bulk != bytes) dst[bulk / 8] = __ldg(cloud + lo * 3 + bulk / 8);
+            mbar_expect_tx(&s_full[p_stage], bulk);
+            bulk_g2s(dst, cloud + lo * 3, bulk, &s_full[p_stage]);
         }
         p_tile += gridDim.x;
         if (++p_stage == kStages) {

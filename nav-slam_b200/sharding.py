@@ -6,8 +6,8 @@ The path shards in exactly two ways, both without touching the kernels:
     the data path (poses / CSVs are gathered by the host afterwards);
   * large-map queries (config 5b): the map is replicated (rank 0 broadcasts the points, every
     rank builds the same flat kd-tree -- the build is deterministic and takes milliseconds), the
-    query set is cut into `world` contiguous shards, and ONE all_gather of (idx:int32, dist:f64)
-    reassembles the answers on every rank.
+    query set is cut into `world` contiguous shards, and ONE all_gather of packed (dist:f64, idx:int32)
+    records reassembles the answers on every rank.
 
 Per-row maps of the SLAM step (<= cols points) are never worth sharding.  One process per GPU;
 torch.distributed (NCCL over NVLink on GPUs, gloo on CPU for the tests) is only the plumbing.
@@ -69,32 +69,47 @@ def sharded_nn(nn_fn: Callable, queries, *, group=None, device=None):
     return idx, dd
 
 
+_PACKED = {}   # (device, world, shard size) -> byte buffer of the packed exchange
+
+
 def sharded_nn_into(nn_into: Callable, queries, idx_out, dist_out, *, group=None):
-    """The same exchange without any packing work, for the hot loop: idx_out [nq] int32 and dist_out [nq]
-    float64 are preallocated on the collective's device (same shapes on every rank); nn_into(q_shard,
-    idx_view, dist_view) writes this rank's contiguous shard straight into its slice of them, and two
-    in-place all_gathers (the slice is the rank's send buffer) complete both arrays on every rank.
-    Needs equal shards (nq % world == 0); otherwise the padded path of sharded_nn() is used."""
+    """The same exchange for the hot loop, with ONE collective and no packing kernels in front of it:
+    idx_out [nq] int32 and dist_out [nq] float64 are preallocated on the collective's device (same shapes on
+    every rank).  A persistent byte buffer holds, for every rank r, the record [dist: m x f64 | idx: m x i32]
+    of its contiguous shard (m = nq / world); nn_into(q_shard, idx_view, dist_view) writes this rank's
+    answers straight into the views of its own record, one in-place all_gather (the record is the rank's
+    send buffer) completes the buffer on every rank, and two strided copies unpack it into idx_out /
+    dist_out.  Needs equal shards (nq % world == 0, m even); otherwise the padded path of sharded_nn()."""
+    import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     nq = int(queries.shape[0])
     lo, hi = shard_bounds(nq, world, rank)
-    if world > 1 and nq % world != 0:
+    if world == 1:
+        nn_into(queries, idx_out, dist_out)
+        return idx_out, dist_out
+    m = nq // world
+    if nq % world != 0 or m % 2 != 0:
         def nn_fn(qs):
-            m = int(qs.shape[0])
-            nn_into(qs, idx_out[lo:lo + m], dist_out[lo:lo + m])
-            return idx_out[lo:lo + m].clone(), dist_out[lo:lo + m].clone()
+            k = int(qs.shape[0])
+            nn_into(qs, idx_out[lo:lo + k], dist_out[lo:lo + k])
+            return idx_out[lo:lo + k].clone(), dist_out[lo:lo + k].clone()
         i, d = sharded_nn(nn_fn, queries, group=group)
         idx_out.copy_(i)
         dist_out.copy_(d)
         return idx_out, dist_out
-    nn_into(queries[lo:hi], idx_out[lo:hi], dist_out[lo:hi])
-    if world > 1:
-        on_cpu = idx_out.device.type == "cpu"   # gloo wants distinct send / receive storage
-        dist.all_gather_into_tensor(idx_out, idx_out[lo:hi].clone() if on_cpu else idx_out[lo:hi], group=group)
-        dist.all_gather_into_tensor(dist_out, dist_out[lo:hi].clone() if on_cpu else dist_out[lo:hi], group=group)
+    key = (str(idx_out.device), world, m)
+    packed = _PACKED.get(key)
+    if packed is None:
+        packed = _PACKED[key] = torch.empty((world, 12 * m), dtype=torch.uint8, device=idx_out.device)
+    mine = packed[rank]
+    nn_into(queries[lo:hi], mine[8 * m:].view(torch.int32), mine[: 8 * m].view(torch.float64))
+    on_cpu = idx_out.device.type == "cpu"   # gloo wants distinct send / receive storage
+    dist.all_gather_into_tensor(packed.view(-1), mine.clone() if on_cpu else mine, group=group)
+    dist_out.view(world, m).copy_(packed[:, : 8 * m].view(torch.float64))
+    idx_out.view(world, m).copy_(packed[:, 8 * m:].view(torch.int32))
     return idx_out, dist_out
 
 

@@ -58,6 +58,8 @@ static nav_ctx *default_ctx(void) {
     return g_default_ctx;
 }
 
+static void release_all(void);
+
 static int slot_of(SLAM_attr *attr, int create) {
     int free_slot = -1;
     for (int i = 0; i < MAX_ATTRS; ++i) {
@@ -72,6 +74,11 @@ static int slot_of(SLAM_attr *attr, int create) {
     g_slots[free_slot].attr = attr;
     g_slots[free_slot].ctx = nav_create(MAX_ROWS, MAX_COLS, 0, 1);
     if (!g_slots[free_slot].ctx) die("nav_create");
+    static int at_exit_registered;
+    if (!at_exit_registered) { /* after the first CUDA call, so that it runs before the runtime's own teardown */
+        at_exit_registered = 1;
+        atexit(release_all);
+    }
     for (int r = 0; r < MAX_ROWS; ++r) {
         shim_handle *h = &g_slots[free_slot].rows[r];
         memset(h, 0, sizeof(*h));
@@ -85,6 +92,24 @@ static int slot_of(SLAM_attr *attr, int create) {
 struct nav_ctx *navslam_context_of(SLAM_attr *attr) {
     int s = slot_of(attr, 0);
     return s < 0 ? NULL : g_slots[s].ctx;
+}
+
+/* The reference never frees its row trees (src/slam.c:167-172 leaks them) and has no teardown call, so a
+ * slot -- a nav_ctx with a few hundred MB of device buffers at 64x2048 -- would otherwise live for ever.
+ * navslam_release() gives a SLAM_attr's slot back (init_slam on the same address re-uses its slot anyway);
+ * whatever is still held at exit is destroyed by the atexit handler. */
+void navslam_release(SLAM_attr *attr) {
+    int s = slot_of(attr, 0);
+    if (s < 0) return;
+    nav_destroy(g_slots[s].ctx);
+    memset(&g_slots[s], 0, sizeof(g_slots[s]));
+}
+
+static void release_all(void) {
+    for (int i = 0; i < MAX_ATTRS; ++i)
+        if (g_slots[i].attr) navslam_release(g_slots[i].attr);
+    if (g_default_ctx) nav_destroy(g_default_ctx);
+    g_default_ctx = NULL;
 }
 
 static void publish_rows(int s) {

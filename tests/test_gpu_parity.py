@@ -706,3 +706,173 @@ def test_sequence_dev_on_legacy_default_stream(pkg, oracle, synth):
     finally:
         ctx.close()
         slam.close()
+
+
+# ------------------------------------------------------------------ round 2 additions --------
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,n", [((5, 33), 1001), ((3, 67), 1501), ((5, 33), 1000)])
+def test_labels_batch_odd_point_count_takes_the_tma_path(pkg, oracle, shape, n):
+    """A batch with an ODD number of points ends in a tile whose byte count is 8 mod 16, which a bulk copy
+    cannot move (sizes must be multiples of 16): the producer stores the trailing double itself.  The batch
+    is large enough (>= 4 tiles per SM) for launch_labels to choose k_labels_tma."""
+    torch = pytest.importorskip("torch")
+    r, c = shape
+    rng = np.random.default_rng(r * 1000 + c + n)
+    base = np.cumsum(rng.normal(0, 30, size=(n, r, c, 3)), axis=2)  # rough polylines: a healthy mix of labels
+    assert (n * r * c) % 2 == (n % 2)
+    ctx = pkg.Context(r, c, device=0)
+    d = torch.from_numpy(base).cuda()
+    lab = torch.full((n, r, c), -7, dtype=torch.int32, device="cuda")
+    ctx.extract_feature_batch_dev(d.data_ptr(), n, lab.data_ptr())
+    torch.cuda.synchronize()
+    got = lab.cpu().numpy()
+    for i in list(range(0, n, max(n // 23, 1))) + [n - 1, n - 2]:   # the last images hold the odd tail
+        assert np.array_equal(got[i], oracle.extract_feature(base[i])), i
+    assert set(np.unique(got)) <= {0, 1}
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_async_wait_brings_all_results_back_into_the_context(pkg, oracle, synth):
+    """After nav_frontend_wait the device-resident results (nav_frame_results_dev) are those of the last
+    pipelined frame: labels AND nn_idx / nn_dist (round-1 advisor finding)."""
+    torch = pytest.importorskip("torch")
+    r, c, n = 16, 1800, 4
+    ctx = pkg.Context(r, c, device=0)
+    clouds = torch.from_numpy(np.stack([synth.room_frame(r, c, f) for f in range(n)])).pin_memory()
+    outs = [torch.empty(r * c * 16, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    z = np.zeros(6)
+    ctx.slam_init(z, clouds[0].numpy())
+    last = z
+    for f in range(1, n):
+        final = last + np.array([50.0, 0, 0, 0, 0, 0])
+        p0 = outs[f & 1].data_ptr()
+        ctx.frontend_frame_async(clouds[f].data_ptr(), final + 1.0, last, final, p0, p0 + r * c * 4, p0 + r * c * 8, None)
+        last = final
+    ctx.frontend_wait()
+    res = ctx.frame_results_dev()
+    host = outs[(n - 1) & 1].numpy()
+    # wrap the context's raw device pointers for torch through the CUDA array interface
+    class Raw:
+        def __init__(self, ptr, n, typestr):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+    lab = torch.as_tensor(Raw(res.labels, r * c, "<i4"), device="cuda").cpu().numpy()
+    idx = torch.as_tensor(Raw(res.nn_idx, r * c, "<i4"), device="cuda").cpu().numpy()
+    dist = torch.as_tensor(Raw(res.nn_dist, r * c, "<f8"), device="cuda").cpu().numpy()
+    assert np.array_equal(lab, host[: r * c * 4].view(np.int32))
+    assert np.array_equal(idx, host[r * c * 4: r * c * 8].view(np.int32))
+    assert np.array_equal(dist, host[r * c * 8:].view(np.float64))
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(8, 8), (16, 1800), (5, 33)])
+def test_submit_depth_input_and_label_masks(pkg, oracle, synth, shape):
+    """nav_frontend_submit with the L5 depth matrix as input (utils/pointcloud.c:8 on the device) and the
+    labels returned as 16-bit masks: same labels / NN / clouds as the oracle, frame for frame, pipelined."""
+    torch = pytest.importorskip("torch")
+    r, c = shape
+    n = 6
+    ctx = pkg.Context(r, c, device=0)
+    slam = oracle.slam(r, c, 1)
+    rng = np.random.default_rng(r + c)
+    depth = np.stack([(3000 + 40 * np.sin(np.arange(c) / 9.0)[None, :] + rng.integers(-6, 7, size=(r, c)) - 15 * f)
+                      for f in range(n)]).astype(np.int32)
+    depth[2, 0, :3] = 0
+    clouds = [oracle.convert(d) for d in depth]
+    h_depth = torch.from_numpy(depth).pin_memory()
+    nch = (c + 15) // 16
+    mask = torch.zeros((n, r, nch), dtype=torch.int32).pin_memory()
+    idx = torch.empty((n, r, c), dtype=torch.int32).pin_memory()
+    dist = torch.empty((n, r, c), dtype=torch.float64).pin_memory()
+    feat = torch.empty((n, r, c), dtype=torch.int32).pin_memory()
+    glob = torch.empty((n, r, c, 3), dtype=torch.float64).pin_memory()
+    conv = torch.empty((n, r, c, 3), dtype=torch.float64).pin_memory()
+    z = np.zeros(6)
+    ctx.slam_init(z, clouds[0])
+    slam.init(z, clouds[0])
+    poses, last = [], z
+    for f in range(1, n):
+        pred = last + np.array([-14.0, 0.5, 0.0, 0.0, 0.0, 0.1])
+        final = last + np.array([-15.0, 0.0, 0.0, 0.0, 0.0, 0.0])
+        poses.append((pred, last, final))
+        kw = dict(distances=h_depth[f].data_ptr(), mask_out=mask[f].data_ptr(), nn_idx_out=idx[f].data_ptr(),
+                  nn_dist_out=dist[f].data_ptr())
+        if f % 2:   # odd frames ask for everything, even frames for the compact set only
+            kw.update(feature_out=feat[f].data_ptr(), global_out=glob[f].data_ptr(), cloud_out=conv[f].data_ptr())
+        ctx.frontend_submit(pred, last, final, **kw)
+        last = final
+    ctx.frontend_wait()
+    for f in range(1, n):
+        ofeat, oidx, odist, og = slam.frontend_frame(clouds[f], *poses[f - 1])
+        m = mask[f].numpy().view(np.uint32)
+        bits = ((m[:, :, None] >> np.arange(16, dtype=np.uint32)) & 1).reshape(r, nch * 16)[:, :c]
+        assert np.array_equal(bits.astype(np.int32), ofeat), f
+        assert np.array_equal(idx[f].numpy(), oidx) and np.array_equal(dist[f].numpy(), odist)
+        if f % 2:
+            assert np.array_equal(feat[f].numpy(), ofeat) and np.array_equal(glob[f].numpy(), og)
+            assert np.array_equal(conv[f].numpy(), clouds[f])
+    with pytest.raises(pkg.NavError):   # exactly one input
+        ctx.frontend_submit(z, z, z, nn_idx_out=idx[0].data_ptr())
+    ctx.close()
+    slam.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,frames,use_depth", [((64, 2048), 6, False), ((16, 1800), 8, False), ((8, 8), 8, True)])
+def test_closed_loop_with_prefetch_equals_blocking_loop(pkg, oracle, synth, shape, frames, use_depth):
+    """nav_slam_prefetch + nav_slam_localization_fast + nav_slam_mapping(NULL, NULL) with pose feedback: the
+    poses are bit-identical to the same loop without prefetch (the statistics are summed in a fixed order),
+    agree with the reference's sequential Adam loop to rounding, and the final map equals the oracle's."""
+    torch = pytest.importorskip("torch")
+    r, c = shape
+    if use_depth:
+        depth = np.stack([synth.l5_depth_frame(f, r, c) for f in range(frames)])
+        clouds = np.stack([oracle.convert(d) for d in depth])
+        h_depth = torch.from_numpy(depth).pin_memory()
+    else:
+        clouds = np.stack([synth.room_frame(r, c, f) for f in range(frames)])
+    h = torch.from_numpy(clouds).pin_memory()
+    step = np.array([-19.0, 0.3, 0.0, 0, 0, 0]) if use_depth else np.array([46.0, 2.0, -1.0, 0.0, 0.0, 0.0])
+
+    def run(prefetch):
+        ctx = pkg.Context(r, c, device=0)
+        ctx.slam_init(np.zeros(6), clouds[0], want_global=False)
+        poses, last = [], np.zeros(6)
+        def pf(f):
+            if use_depth:
+                ctx.slam_prefetch(depth_ptr=h_depth[f].data_ptr())
+            else:
+                ctx.slam_prefetch(cloud_ptr=h[f].data_ptr())
+        if prefetch:
+            pf(1)
+        for f in range(1, frames):
+            if prefetch and f + 1 < frames:
+                pf(f + 1)
+            if prefetch:
+                p, err, n = ctx.slam_localization_fast_ptr(None if use_depth else h[f].data_ptr(), last + step, last)
+            else:
+                p, err, n = ctx.slam_localization_fast(clouds[f], last + step, last)
+            ctx.slam_mapping(p, None, want_global=False)
+            poses.append((p, err, n))
+            last = p
+        g = ctx.slam_mapping(last, None)   # same pose again: downloads the final map
+        ctx.close()
+        return poses, g
+
+    a, ga = run(True)
+    b, gb = run(False)
+    for (pa, ea, na), (pb, eb, nb) in zip(a, b):
+        assert np.array_equal(pa, pb) and ea == eb and na == nb
+    assert np.array_equal(ga, gb)
+    slam = oracle.slam(r, c, 1)
+    slam.init(np.zeros(6), clouds[0])
+    last = np.zeros(6)
+    for f in range(1, frames):
+        p_or, corr, err_or, _ = slam.localize(clouds[f], last + step, last)
+        assert a[f - 1][2] == corr.shape[0]
+        assert np.allclose(a[f - 1][0], p_or, rtol=1e-9, atol=1e-6)
+        og = slam.map(a[f - 1][0], clouds[f])   # feed OUR pose back so that the maps stay comparable bit for bit
+        last = a[f - 1][0]
+    assert np.array_equal(ga, og)
+    slam.close()
