@@ -308,20 +308,27 @@ def run_shim_leg(args):
     n = args.shim_frames
     frames = pkg.synth.room_sequence(ROWS, COLS, n + 1, cfg=3, seq=0)
     shim = sb.ShimSlam(ROWS, COLS)
-    pcs = [shim.pack_cloud(frames[f], ts=f) for f in range(n + 1)]
+    # ONE PointCloud buffer refilled for every frame, as the reference's handlers do (src/main.c:250,308)
+    pc = shim.pack_cloud(frames[0], ts=0)
+
+    def load(f):
+        pc[:4] = np.frombuffer(np.int32(f).tobytes(), dtype=np.uint8)
+        pc[8:] = frames[f].reshape(-1).view(np.uint8)
+        return pc
     devnull = os.open(os.devnull, os.O_WRONLY)
     saved = os.dup(1)
     sys.stdout.flush()
     os.dup2(devnull, 1)
     try:
-        shim.init_slam(np.zeros(6), pcs[0])
+        shim.init_slam(np.zeros(6), load(0))
         last = np.zeros(6)
         ts = []
         for f in range(1, n + 1):
             pred = last + np.array([48.0, 0.5, 0.0, 0.0, 0.0, 0.0])
+            load(f)
             t0 = time.perf_counter()
-            p = shim.slam_localization(pcs[f], pred, last)
-            shim.slam_mapping(p, pcs[f])
+            p = shim.slam_localization(pc, pred, last)
+            shim.slam_mapping(p, pc)
             ts.append(time.perf_counter() - t0)
             last = p
     finally:
@@ -331,7 +338,8 @@ def run_shim_leg(args):
     t = float(np.median(ts[skip:]))
     out = {"ms_per_frame": 1e3 * t, "frames_per_s": 1.0 / t, "frames": n, "pose_x": float(last[0]),
            "pose_x_truth": 50.0 * n, "rms_mm": shim.error,
-           "NAVSLAM_ADAM": os.environ.get("NAVSLAM_ADAM", ""), "NAVSLAM_TRUST_FRAME": os.environ.get("NAVSLAM_TRUST_FRAME", "")}
+           "NAVSLAM_ADAM": os.environ.get("NAVSLAM_ADAM", ""), "NAVSLAM_TRUST_FRAME": os.environ.get("NAVSLAM_TRUST_FRAME", ""),
+           "NAVSLAM_PIN": os.environ.get("NAVSLAM_PIN", "")}
     with open(args.shim_out, "w") as f:
         json.dump(out, f)
     shim.release()
@@ -342,11 +350,13 @@ def shim_legs():
     out = {}
     for name, env, n in (("default", {}, 12),
                          ("stats", {"NAVSLAM_ADAM": "stats"}, 60),
-                         ("stats_trust_frame", {"NAVSLAM_ADAM": "stats", "NAVSLAM_TRUST_FRAME": "1"}, 60)):
+                         ("stats_trust_frame", {"NAVSLAM_ADAM": "stats", "NAVSLAM_TRUST_FRAME": "1"}, 60),
+                         ("stats_trust_frame_pinned", {"NAVSLAM_ADAM": "stats", "NAVSLAM_TRUST_FRAME": "1",
+                                                       "NAVSLAM_PIN": "1"}, 60)):
         with tempfile.NamedTemporaryFile(suffix=".json", delete=False) as tf:
             path = tf.name
         e = dict(os.environ)
-        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "NAVSLAM_ADAM", "NAVSLAM_TRUST_FRAME"):
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "NAVSLAM_ADAM", "NAVSLAM_TRUST_FRAME", "NAVSLAM_PIN"):
             e.pop(k, None)
         e.update(env)
         try:
@@ -630,12 +640,12 @@ def run_gpu_arm(args):
             cur = triangle(i, n_res)
             check((L.nav_slam_prefetch_depth if depth else L.nav_slam_prefetch)(ctx.h, src(cur)))
 
-        def one(i):
+        def one(i, ahead=True):
             cur, prev = triangle(i, n_res), triangle(i - 1, n_res)
             last = state["last"]
             pred = last + (pose_of(cur) - pose_of(prev)) + np.array([-2.0, 0.5, 0.0, 0.0, 0.0, 0.0])
             pl, pp = pos_c(last), pos_c(pred)
-            if prefetch:
+            if prefetch and ahead:
                 pf(i + 1)
             check(L.nav_slam_localization_fast(ctx.h, (None if depth else src(cur)) if prefetch else src(cur),
                                                C.byref(pp), C.byref(pl), C.byref(out), C.byref(err), C.byref(ncorr)))
@@ -654,7 +664,7 @@ def run_gpu_arm(args):
         barrier()
         wall = reduce_max([time.perf_counter() - t0])[0]
         if prefetch:   # consume the frame prefetched last so that the context is left clean
-            one(W + 1 + n_steps)
+            one(W + 1 + n_steps, ahead=False)
         ctx.synchronize()
         cur = triangle(W + n_steps + (1 if prefetch else 0), n_res)
         return {"us_per_frame": 1e6 * wall / n_steps, "frames_per_s": world * n_steps / wall, "steps_timed": n_steps,

@@ -50,6 +50,9 @@ const char *nav_last_error(void);
 int nav_device_count(void);          /* 0 when no CUDA device is usable */
 void *nav_host_alloc(size_t bytes);  /* pinned host memory (cudaHostAlloc) */
 void nav_host_free(void *p);
+/* page-lock / release memory the caller already owns (cudaHostRegister): pinned buffers are DMA'd directly */
+int nav_host_register(void *p, size_t bytes);
+int nav_host_unregister(void *p);
 
 /* ---- context ------------------------------------------------------------------- */
 /* n_seq = number of independent sequences processed side by side (1..NAV_MAX_SEQ);

@@ -54,6 +54,7 @@ EXPORTS = [
     "nav_l9_csv_read", "nav_csv_header", "nav_csv_format_frame", "nav_csv_format_frame_gpu",
     "nav_csv_format_frame_dev", "nav_l5_json_read", "nav_imu_json_read",
     "nav_frontend_submit", "nav_frontend_frame_depth_async", "nav_slam_prefetch", "nav_slam_prefetch_depth",
+    "nav_host_register", "nav_host_unregister",
 ]
 
 
@@ -77,6 +78,8 @@ def load_library(build_if_missing: bool = True):
     L.nav_host_alloc.restype = C.c_void_p
     L.nav_host_alloc.argtypes = [C.c_size_t]
     L.nav_host_free.argtypes = [C.c_void_p]
+    L.nav_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.nav_host_unregister.argtypes = [C.c_void_p]
     L.nav_create.restype = C.c_void_p
     L.nav_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.nav_destroy.argtypes = [C.c_void_p]

@@ -17,7 +17,7 @@ SHIM = os.path.join(HERE, "shim")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libnavslam_b200.so")
 
-CU_SOURCES = ["stencil.cu", "rowmap.cu", "kdtree.cu", "bf_tc.cu", "io.cu", "csvfmt.cu", "capi.cu"]
+CU_SOURCES = ["stencil.cu", "rowmap.cu", "kdbuild.cu", "kdtree.cu", "bf_tc.cu", "io.cu", "csvfmt.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",  # nothing that decides an output may be contracted into an FMA

@@ -442,17 +442,20 @@ cudaError_t bf_nn_tc(const double *d_pts, size_t n, const double *d_queries, siz
     const size_t dyn = 120 * 1024;
     static_assert(kTcABytes + kTcStages * kTcBBytes <= 120 * 1024, "operand ring exceeds the dynamic smem request");
     static bool configured = false;
+    int device = 0;
     if (n_tiles > 0x7fffffffLL || q_tiles > 0x7fffffffLL) return cudaErrorInvalidValue;
     if (!configured) {
         TC_CHECK(cudaFuncSetAttribute(k_tc_tiles<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         TC_CHECK(cudaFuncSetAttribute(k_tc_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         configured = true;
     }
-    TC_CHECK(cudaMallocAsync(&stats, 9 * sizeof(unsigned long long), stream));
-    TC_CHECK(cudaMallocAsync(&aop, (size_t)nq_pad * kTcK * 2, stream));
-    TC_CHECK(cudaMallocAsync(&bop, (size_t)n_pad * kTcK * 2, stream));
-    TC_CHECK(cudaMallocAsync(&rowmax, (size_t)nq_pad * 4, stream));
-    TC_CHECK(cudaMallocAsync(&mask, (size_t)n_tiles * nq_pad, stream));
+    TC_CHECK(cudaGetDevice(&device));
+    // workspace from the library's own stream-ordered pool (kd_pool_alloc, kdbuild.cu)
+    TC_CHECK(kd_pool_alloc((void **)&stats, 9 * sizeof(unsigned long long), device, stream));
+    TC_CHECK(kd_pool_alloc((void **)&aop, (size_t)nq_pad * kTcK * 2, device, stream));
+    TC_CHECK(kd_pool_alloc((void **)&bop, (size_t)n_pad * kTcK * 2, device, stream));
+    TC_CHECK(kd_pool_alloc((void **)&rowmax, (size_t)nq_pad * 4, device, stream));
+    TC_CHECK(kd_pool_alloc((void **)&mask, (size_t)n_tiles * nq_pad, device, stream));
     {
         const int g1 = (int)((n + 255) / 256 < (size_t)sm_count * 8 ? (n + 255) / 256 : (size_t)sm_count * 8);
         const int g2 = (int)((n_pad + 127) / 128 < (long long)sm_count * 16 ? (n_pad + 127) / 128 : (long long)sm_count * 16);

@@ -75,6 +75,25 @@ extern "C" void *nav_host_alloc(size_t bytes) {
 extern "C" void nav_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }
+// page-lock memory the caller already owns (cudaHostRegister), so that the host-buffer calls DMA it
+// directly instead of staging it through a bounce buffer
+extern "C" int nav_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return fail("nav_host_register: null argument");
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail("nav_host_register(%p, %zu): %s", p, bytes, cudaGetErrorString(e));
+    }
+    return 0;
+}
+extern "C" int nav_host_unregister(void *p) {
+    if (!p) return 0;
+    if (cudaHostUnregister(p) != cudaSuccess) {
+        cudaGetLastError();
+        return fail("nav_host_unregister(%p) failed", p);
+    }
+    return 0;
+}
 
 // ------------------------------------------------------------------ staging -----------------
 struct PendingOut {
@@ -666,6 +685,7 @@ extern "C" int nav_slam_init(nav_ctx *c, const nav_pos *pos, const nav_point *cl
     CTX_ENTER(c, "nav_slam_init");
     if (!pos || !cloud) return fail("nav_slam_init: null argument");
     if (c->stage.reserve(c->ntot * 48 + 1024, c->stream)) return fail("nav_slam_init: staging");
+    for (auto &ps : c->pre) ps.pending = false;  // a new sequence starts: frames prefetched for the old one are dropped
     if (upload_cloud(c, cloud, "nav_slam_init")) return 1;
     run_labels(c, c->d_cloud, c->d_labels, nullptr, c->n_seq);
     run_map(c, c->d_cloud, c->d_labels, pose_batch(c, pos, nullptr));
@@ -680,6 +700,7 @@ extern "C" int nav_slam_init(nav_ctx *c, const nav_pos *pos, const nav_point *cl
 extern "C" int nav_slam_init_dev(nav_ctx *c, const void *dev_cloud, const nav_pos *pos) {
     CTX_ENTER(c, "nav_slam_init_dev");
     if (!pos || !dev_cloud) return fail("nav_slam_init_dev: null argument");
+    for (auto &ps : c->pre) ps.pending = false;
     run_labels(c, (const double *)dev_cloud, c->d_labels, nullptr, c->n_seq);
     run_map(c, (const double *)dev_cloud, c->d_labels, pose_batch(c, pos, nullptr));
     c->cloud_resident = false;
@@ -1372,13 +1393,6 @@ static nav_kdtree *kd_new(int device, size_t n, bool on_user_stream, cudaStream_
         return nullptr;
     }
     CUP(cudaSetDevice(device));
-    {   // the build takes its workspace from the stream-ordered pool: keep freed blocks cached
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long thr = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-    }
     nav_kdtree *t = new nav_kdtree();
     t->device = device;
     t->n = n;
@@ -1387,10 +1401,13 @@ static nav_kdtree *kd_new(int device, size_t n, bool on_user_stream, cudaStream_
     t->user_stream = user_stream;
     bool ok = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking) == cudaSuccess;
     const cudaStream_t as = on_user_stream ? user_stream : t->stream;  // the stream the build runs on
-    ok = ok && cudaMallocAsync((void **)&t->d_bbox, 64, as) == cudaSuccess;  // 48 B box + 8 B work-queue counter
+    // tree storage and the build's workspace come from the library's own stream-ordered pool
+    // (kd_pool_alloc): no device-wide synchronisation, no page mapping per build, and the device's
+    // default pool is left as the application configured it
+    ok = ok && kd_pool_alloc((void **)&t->d_bbox, 64, device, as) == cudaSuccess;  // 48 B box + 8 B work-queue counter
     if (ok && n)
-        ok = cudaMallocAsync((void **)&t->d_nodes, n * sizeof(KdNode), as) == cudaSuccess &&
-             cudaMallocAsync((void **)&t->d_pts, n * 24, as) == cudaSuccess;
+        ok = kd_pool_alloc((void **)&t->d_nodes, n * sizeof(KdNode), device, as) == cudaSuccess &&
+             kd_pool_alloc((void **)&t->d_pts, n * 24, device, as) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
         fail("nav_kdtree_build: device allocation for %zu points failed", n);
@@ -1540,11 +1557,6 @@ extern "C" int nav_bruteforce_nn_batch_dev(int device, const void *dev_points, s
     if (use_tensor_cores) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            unsigned long long thr = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
         static const bool want_stats = getenv("NAV_TC_STATS") != nullptr;  // prints the re-rank volume (forces a sync)
         unsigned long long evals = 0;
         CU(bf_nn_tc((const double *)dev_points, n, (const double *)dev_queries, nq, (int *)dev_idx, (double *)dev_dist,

@@ -1,4 +1,5 @@
-// kdtree.cu -- flat implicit kd-tree for large maps (a5) and batched exact 1-NN (a6).
+// kdtree.cu -- batched exact 1-NN (a6) on the flat implicit kd-tree for large maps, and the exact
+// binary64 brute force.
 //
 // Reference: utils/kdtree.c:65-82 builds a pointer tree by recursive median split (axis =
 // depth % 3, median index n/2, children on [0,m) and [m+1,n)) with one malloc per node and an
@@ -9,20 +10,8 @@
 // as the reference, so with distinct keys it is the same tree.  Nodes are 32-byte records
 // {x,y,z,orig_index} (one DRAM sector each, subtrees contiguous in memory).
 //
-// Build, level by level, all segments of a level at once (no recursion, no per-node allocation):
-//   1. three index lists, each sorted along one axis (radix sort of order-preserving 64-bit keys);
-//   2. every segment picks its split axis -- kSplitCyclic: level % 3 like the reference (the exported
-//      tree then is the reference's tree); kSplitWidest (default): the axis of largest extent, read off
-//      the two ends of the segment in each sorted list.  Maps made of surfaces (walls, floors) have
-//      axes along which a segment has no extent; cycling through them doubles the search at every such
-//      level, which the widest-extent rule avoids (4x fewer node visits on the accumulated room map);
-//   3. the list of that axis holds the segment sorted, so its median is the middle element: mark each
-//      point left / median / right;
-//   4. all three lists are stably partitioned inside every segment (one prefix sum of packed
-//      left/median counts over the 3n positions + one scatter), which keeps them sorted for the levels
-//      below (for the list of the split axis this is the identity).
-// After ceil(log2 n) levels the three lists coincide and are the in-order layout.  The split axis is
-// stored in each node, so the search does not care which rule built the tree.
+// The build lives in kdbuild.cu (radix select of the median + one partition pass per level).  The split
+// axis is stored in each node, so the search does not care which rule built the tree.
 //
 // Query: one thread per query.  Child ranges are pure arithmetic on (lo,hi).  Three interchangeable
 // kernels (identical answers, chosen by measurement in kd_nn()): k_kd_nn_stack keeps pending far
@@ -32,11 +21,6 @@
 // scanned as a contiguous run.  Far subtrees are visited iff the rounded plane distance^2 is <= the
 // current best dsq; candidates compare lexicographically on (dsq, original index): exact NN, lowest
 // index on ties.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-#include <thrust/iterator/counting_iterator.h>
-#include <thrust/iterator/transform_iterator.h>
-
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -44,443 +28,6 @@
 #include "nav_kdtree.cuh"
 
 namespace nav {
-
-// ------------------------------------------------------------------------------ build ------
-__device__ __forceinline__ unsigned long long order_key(double v) {
-    unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-}
-
-__global__ void k_make_keys(const double *__restrict__ pts, long long n, unsigned long long *__restrict__ kx,
-                            unsigned long long *__restrict__ ky, unsigned long long *__restrict__ kz,
-                            int *__restrict__ idx) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x) {
-        kx[i] = order_key(pts[i * 3]);
-        ky[i] = order_key(pts[i * 3 + 1]);
-        kz[i] = order_key(pts[i * 3 + 2]);
-        idx[i] = (int)i;
-    }
-}
-
-// segment of position p at `level`: descend from the root range by arithmetic.
-// returns false if p became a node at a shallower level.
-__device__ __forceinline__ bool segment_of(int p, int n, int level, int &lo, int &hi) {
-    lo = 0;
-    hi = n;
-    for (int l = 0; l < level; ++l) {
-        const int mid = lo + ((hi - lo) >> 1);
-        if (p < mid)
-            hi = mid;
-        else if (p == mid)
-            return false;
-        else
-            lo = mid + 1;
-    }
-    return true;
-}
-
-// range of segment number s (bits of s, most significant first, = sides taken from the root) at `level`
-__device__ __forceinline__ bool segment_range(int s, int n, int level, int &lo, int &hi) {
-    lo = 0;
-    hi = n;
-    for (int l = level - 1; l >= 0; --l) {
-        const int mid = lo + ((hi - lo) >> 1);
-        if ((s >> l) & 1)
-            lo = mid + 1;
-        else
-            hi = mid;
-        if (lo >= hi) return false;
-    }
-    return true;
-}
-
-// split axis of every segment of this level, stored at the position its node will take (mid)
-__global__ void k_choose_axis(const double *__restrict__ pts, const int *__restrict__ lists, int n, int level,
-                              int rule, unsigned char *__restrict__ axis_at) {
-    const long long n_seg = 1ll << level;
-    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < n_seg;
-         s += (long long)gridDim.x * blockDim.x) {
-        int lo, hi;
-        if (!segment_range((int)s, n, level, lo, hi)) continue;
-        int axis = level % 3;
-        if (rule == kSplitWidest) {
-            double ext[3];
-            for (int d = 0; d < 3; ++d) {
-                const double first = pts[(long long)lists[(long long)d * n + lo] * 3 + d];
-                const double last = pts[(long long)lists[(long long)d * n + hi - 1] * 3 + d];
-                ext[d] = last - first;
-            }
-            axis = 0;  // ties and NaN extents keep the lowest axis
-            if (ext[1] > ext[axis]) axis = 1;
-            if (ext[2] > ext[axis]) axis = 2;
-        }
-        axis_at[lo + ((hi - lo) >> 1)] = (unsigned char)axis;
-    }
-}
-
-// side codes: 0 left, 1 median (becomes the node), 2 right
-__global__ void k_mark(const int *__restrict__ lists, int n, int level, const unsigned char *__restrict__ axis_at,
-                       int *__restrict__ seg_lo, int *__restrict__ seg_mid, unsigned char *__restrict__ side) {
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        int lo, hi;
-        if (!segment_of(p, n, level, lo, hi)) {
-            seg_lo[p] = -1;
-            seg_mid[p] = -1;
-            continue;
-        }
-        const int mid = lo + ((hi - lo) >> 1);
-        seg_lo[p] = lo;
-        seg_mid[p] = mid;
-        side[lists[(long long)axis_at[mid] * n + p]] = p < mid ? 0 : (p == mid ? 1 : 2);
-    }
-}
-
-// the three lists are handled as one array of 3n positions (list a = positions [a*n, (a+1)*n)).
-// Input of the prefix sum, evaluated on the fly by the scan kernel (no flag array is materialised):
-// packed counters, low word = "goes left", high word = "is the median", of the point at position g.
-struct SideFlag {
-    const int *lists;
-    const int *seg_lo;
-    const unsigned char *side;
-    long long n;
-    __device__ __forceinline__ unsigned long long operator()(long long g) const {
-        const long long p = g < n ? g : (g < 2 * n ? g - n : g - 2 * n);
-        if (seg_lo[p] < 0) return 0ull;
-        const unsigned char sd = side[lists[g]];
-        return sd == 0 ? 1ull : (sd == 1 ? (1ull << 32) : 0ull);
-    }
-};
-
-__global__ void k_scatter(const int *__restrict__ lists, int *__restrict__ lists_out, int n,
-                          const int *__restrict__ seg_lo, const int *__restrict__ seg_mid,
-                          const unsigned char *__restrict__ side, const unsigned long long *__restrict__ scan) {
-    const long long base = (long long)blockIdx.y * n;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        const long long g = base + p;
-        const int idx = lists[g];
-        const int lo = seg_lo[p];
-        if (lo < 0) {
-            lists_out[g] = idx;
-            continue;
-        }
-        const int mid = seg_mid[p];
-        const unsigned long long rel = scan[g] - scan[base + lo];
-        const int lefts = (int)(rel & 0xffffffffull), meds = (int)(rel >> 32);
-        const unsigned char s = side[idx];
-        int dst;
-        if (s == 0)
-            dst = lo + lefts;
-        else if (s == 1)
-            dst = mid;
-        else
-            dst = mid + 1 + ((p - lo) - lefts - meds);
-        lists_out[base + dst] = idx;
-    }
-}
-
-__global__ void k_emit_nodes(const double *__restrict__ pts, const int *__restrict__ order, int n,
-                             const unsigned char *__restrict__ axis_at, KdNode *__restrict__ nodes) {
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        const int i = order[p];
-        KdNode nd;
-        nd.x = pts[(long long)i * 3];
-        nd.y = pts[(long long)i * 3 + 1];
-        nd.z = pts[(long long)i * 3 + 2];
-        nd.idx = i;
-        nd.axis = axis_at[p];
-        nodes[p] = nd;
-    }
-}
-
-// ---- finisher: once every segment of a level holds at most kFinSeg points, one CTA takes one segment
-// and builds the whole subtree below it in shared memory -- the same choose / mark / stable partition
-// steps as the global levels, with __syncthreads() where those have kernel boundaries -- and writes the
-// finished nodes.  Replaces the last ~11 levels (5 launches and several passes over all 3n list entries
-// each) by one launch.
-constexpr int kFinSeg = 2048;
-constexpr int kFinThreads = 512;
-constexpr int kFinItems = kFinSeg / kFinThreads;
-// lists (2 x 3 x int) + prefix sums + global ids + split axes + side codes
-constexpr size_t kFinSmemBytes = sizeof(int) * 6 * kFinSeg + sizeof(unsigned) * kFinSeg + sizeof(int) * kFinSeg + 2 * kFinSeg;
-
-// nodes created by the global levels (depth < level0): thread j in [1, 2^level0) is segment j - 2^L of level L
-__global__ void k_emit_top(const double *__restrict__ pts, const int *__restrict__ list0, int n, int level0,
-                           const unsigned char *__restrict__ axis_at, KdNode *__restrict__ nodes) {
-    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (j < 1 || j >= (1ll << level0)) return;
-    const int L = 63 - __clzll(j);
-    int lo, hi;
-    if (!segment_range((int)(j - (1ll << L)), n, L, lo, hi)) return;
-    const int mid = lo + ((hi - lo) >> 1);
-    const int i = list0[mid];
-    KdNode nd;
-    nd.x = pts[(long long)i * 3];
-    nd.y = pts[(long long)i * 3 + 1];
-    nd.z = pts[(long long)i * 3 + 2];
-    nd.idx = i;
-    nd.axis = axis_at[mid];
-    nodes[mid] = nd;
-}
-
-__global__ void __launch_bounds__(kFinThreads, 3)
-k_kd_finish(const double *__restrict__ pts, const int *__restrict__ lists_in, int n, int level0, int split_rule,
-            int *__restrict__ loc, KdNode *__restrict__ nodes) {
-    extern __shared__ __align__(16) unsigned char fin_smem[];
-    int *cur = reinterpret_cast<int *>(fin_smem);        // [3][kFinSeg]
-    int *alt = cur + 3 * kFinSeg;                         // [3][kFinSeg]
-    unsigned *sc = reinterpret_cast<unsigned *>(alt + 3 * kFinSeg);  // [kFinSeg] exclusive prefix, lefts | meds << 16
-    int *gid = reinterpret_cast<int *>(sc + kFinSeg);    // [kFinSeg] local id -> index of the point in the build input
-    unsigned char *ax = reinterpret_cast<unsigned char *>(gid + kFinSeg);  // [kFinSeg] split axis of the node at a position
-    unsigned char *side = ax + kFinSeg;                   // [kFinSeg] left / median / right code per local id
-    __shared__ unsigned s_wsum[kFinThreads / 32];
-    int LO, HI;
-    if (!segment_range((int)blockIdx.x, n, level0, LO, HI)) return;
-    const int m = HI - LO;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // local ids: the i-th entry of the x-sorted list is point i of this CTA; `loc` (n ints of global
-    // scratch, each CTA touches only its own points) translates the two other lists once, after which
-    // every level works on shared memory only
-    for (int i = tid; i < m; i += kFinThreads) {
-        const int g = lists_in[LO + i];
-        gid[i] = g;
-        loc[g] = i;
-        cur[i] = i;
-    }
-    for (int i = tid; i < kFinSeg; i += kFinThreads) ax[i] = 0;
-    __syncthreads();
-    for (int d = 1; d < 3; ++d)
-        for (int i = tid; i < m; i += kFinThreads) cur[d * kFinSeg + i] = loc[lists_in[(long long)d * n + LO + i]];
-    // this thread owns positions 4*tid .. 4*tid+3 (relative to LO); lo_r/hi_r: their current segment,
-    // hi_r < 0 once the position has become a node
-    int lo_r[kFinItems], hi_r[kFinItems];
-#pragma unroll
-    for (int k = 0; k < kFinItems; ++k) {
-        lo_r[k] = 0;
-        hi_r[k] = (kFinItems * tid + k < m) ? m : -1;
-    }
-    __syncthreads();
-    for (int l = 0; (m >> l) >= 2; ++l) {
-        // choose: one thread per segment of this level
-        for (int sgm = tid; sgm < (1 << l); sgm += kFinThreads) {
-            int lo, hi;
-            if (!segment_range(sgm, m, l, lo, hi)) continue;
-            int axis = (level0 + l) % 3;
-            if (split_rule == kSplitWidest) {
-                double ext[3];
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const double first = pts[(long long)gid[cur[d * kFinSeg + lo]] * 3 + d];
-                    const double last = pts[(long long)gid[cur[d * kFinSeg + hi - 1]] * 3 + d];
-                    ext[d] = last - first;
-                }
-                axis = 0;
-                if (ext[1] > ext[axis]) axis = 1;
-                if (ext[2] > ext[axis]) axis = 2;
-            }
-            ax[lo + ((hi - lo) >> 1)] = (unsigned char)axis;
-        }
-        __syncthreads();
-        // mark: left / median / right of every point, read off the list of its segment's split axis
-#pragma unroll
-        for (int k = 0; k < kFinItems; ++k) {
-            if (hi_r[k] < 0) continue;
-            const int p = kFinItems * tid + k, mid = lo_r[k] + ((hi_r[k] - lo_r[k]) >> 1);
-            side[cur[ax[mid] * kFinSeg + p]] = p < mid ? 0 : (p == mid ? 1 : 2);
-        }
-        __syncthreads();
-        // stable partition of the three lists inside every segment
-        for (int d = 0; d < 3; ++d) {
-            unsigned f[kFinItems], run = 0;
-            int idv[kFinItems];
-            unsigned char sdv[kFinItems];
-#pragma unroll
-            for (int k = 0; k < kFinItems; ++k) {
-                const int p = kFinItems * tid + k;
-                idv[k] = p < m ? cur[d * kFinSeg + p] : 0;
-                sdv[k] = 3;
-                f[k] = 0;
-                if (hi_r[k] >= 0) {
-                    sdv[k] = side[idv[k]];
-                    f[k] = sdv[k] == 0 ? 1u : (sdv[k] == 1 ? (1u << 16) : 0u);
-                }
-                run += f[k];
-            }
-            unsigned inc = run;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            if (lane == 31) s_wsum[warp] = inc;
-            __syncthreads();
-            unsigned base = 0;
-            for (int w = 0; w < warp; ++w) base += s_wsum[w];
-            unsigned ex = base + inc - run;
-#pragma unroll
-            for (int k = 0; k < kFinItems; ++k) {
-                sc[kFinItems * tid + k] = ex;
-                ex += f[k];
-            }
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < kFinItems; ++k) {
-                const int p = kFinItems * tid + k;
-                if (p >= m) continue;
-                if (hi_r[k] < 0) {
-                    alt[d * kFinSeg + p] = idv[k];
-                    continue;
-                }
-                const int lo = lo_r[k], mid = lo + ((hi_r[k] - lo) >> 1);
-                const unsigned rel = sc[p] - sc[lo];
-                const int lefts = (int)(rel & 0xffffu), meds = (int)(rel >> 16);
-                const int dst = sdv[k] == 0 ? lo + lefts : (sdv[k] == 1 ? mid : mid + 1 + ((p - lo) - lefts - meds));
-                alt[d * kFinSeg + dst] = idv[k];
-            }
-            __syncthreads();
-        }
-        // descend: every position moves into the child segment that contains it
-#pragma unroll
-        for (int k = 0; k < kFinItems; ++k) {
-            if (hi_r[k] < 0) continue;
-            const int p = kFinItems * tid + k, mid = lo_r[k] + ((hi_r[k] - lo_r[k]) >> 1);
-            if (p < mid)
-                hi_r[k] = mid;
-            else if (p == mid)
-                hi_r[k] = -1;
-            else
-                lo_r[k] = mid + 1;
-        }
-        int *t2 = cur;
-        cur = alt;
-        alt = t2;
-    }
-    for (int p = tid; p < m; p += kFinThreads) {
-        const int i = gid[cur[p]];
-        KdNode nd;
-        nd.x = pts[(long long)i * 3];
-        nd.y = pts[(long long)i * 3 + 1];
-        nd.z = pts[(long long)i * 3 + 2];
-        nd.idx = i;
-        nd.axis = ax[p];
-        nodes[LO + p] = nd;
-    }
-}
-
-#define KD_CHECK(call)                     \
-    do {                                   \
-        cudaError_t e_ = (call);           \
-        if (e_ != cudaSuccess) {           \
-            status = e_;                   \
-            goto done;                     \
-        }                                  \
-    } while (0)
-
-// bounding box of the points from the ends of the three sorted lists: bbox = {lo.xyz, hi.xyz}
-__global__ void k_bbox_from_lists(const double *__restrict__ pts, const int *__restrict__ lists, int n,
-                                  double *__restrict__ bbox) {
-    const int a = threadIdx.x;
-    if (a < 3) {
-        bbox[a] = pts[(long long)lists[(long long)a * n] * 3 + a];
-        bbox[3 + a] = pts[(long long)lists[(long long)a * n + n - 1] * 3 + a];
-    }
-}
-
-cudaError_t kd_build(const double *d_pts, size_t n_sz, KdNode *d_nodes, double *d_bbox, int sm_count,
-                     cudaStream_t stream, uint64_t *launches, int split_rule) {
-    if (n_sz == 0) return cudaSuccess;
-    if (n_sz > (size_t)0x7fffffff) return cudaErrorInvalidValue;
-    const int n = (int)n_sz;
-    cudaError_t status = cudaSuccess;
-    unsigned long long *keys = nullptr, *keys_alt = nullptr, *flags = nullptr;
-    int *idx0 = nullptr, *lists = nullptr, *lists_alt = nullptr, *seg_lo = nullptr, *seg_mid = nullptr;
-    unsigned char *side = nullptr, *axis_at = nullptr;
-    void *tmp = nullptr;
-    size_t tmp_sort = 0, tmp_scan = 0, tmp_bytes = 0;
-    uint64_t nl = 0;
-    const int threads = 256;
-    int grid = (int)((n_sz + threads - 1) / threads);
-    if (grid > sm_count * 16) grid = sm_count * 16;
-
-    KD_CHECK(cudaMallocAsync(&keys, sizeof(unsigned long long) * n_sz * 3, stream));
-    KD_CHECK(cudaMallocAsync(&keys_alt, sizeof(unsigned long long) * n_sz, stream));
-    KD_CHECK(cudaMallocAsync(&flags, sizeof(unsigned long long) * n_sz * 3, stream));
-    KD_CHECK(cudaMallocAsync(&idx0, sizeof(int) * n_sz, stream));
-    KD_CHECK(cudaMallocAsync(&lists, sizeof(int) * n_sz * 3, stream));
-    KD_CHECK(cudaMallocAsync(&lists_alt, sizeof(int) * n_sz * 3, stream));
-    KD_CHECK(cudaMallocAsync(&seg_lo, sizeof(int) * n_sz, stream));
-    KD_CHECK(cudaMallocAsync(&seg_mid, sizeof(int) * n_sz, stream));
-    KD_CHECK(cudaMallocAsync(&side, n_sz, stream));
-    KD_CHECK(cudaMallocAsync(&axis_at, n_sz, stream));
-    KD_CHECK(cudaMemsetAsync(axis_at, 0, n_sz, stream));
-    KD_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, keys, keys_alt, idx0, lists, n, 0, 64, stream));
-    {
-        auto flag_in = thrust::make_transform_iterator(thrust::counting_iterator<long long>(0),
-                                                       SideFlag{lists, seg_lo, side, (long long)n});
-        KD_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, flag_in, flags, 3ll * n, stream));
-    }
-    tmp_bytes = tmp_sort > tmp_scan ? tmp_sort : tmp_scan;
-    KD_CHECK(cudaMallocAsync(&tmp, tmp_bytes, stream));
-
-    k_make_keys<<<grid, threads, 0, stream>>>(d_pts, n, keys, keys + n_sz, keys + 2 * n_sz, idx0);
-    ++nl;
-    for (int a = 0; a < 3; ++a) {
-        KD_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_sort, keys + a * n_sz, keys_alt, idx0,
-                                                 lists + a * n_sz, n, 0, 64, stream));
-        nl += 8;
-    }
-    if (d_bbox) {
-        k_bbox_from_lists<<<1, 32, 0, stream>>>(d_pts, lists, n, d_bbox);
-        ++nl;
-    }
-    {
-        int *cur = lists, *alt = lists_alt;
-        const dim3 grid3((unsigned)grid, 3u);  // blockIdx.y = list
-        // global levels until every segment fits one CTA of the finisher
-        int level0 = 0;
-        while ((n >> level0) > kFinSeg) ++level0;
-        for (int level = 0; level < level0; ++level) {
-            long long sgrid = ((1ll << level) + threads - 1) / threads;
-            if (sgrid > grid) sgrid = grid;
-            k_choose_axis<<<(int)sgrid, threads, 0, stream>>>(d_pts, cur, n, level, split_rule, axis_at);
-            k_mark<<<grid, threads, 0, stream>>>(cur, n, level, axis_at, seg_lo, seg_mid, side);
-            auto flag_in = thrust::make_transform_iterator(thrust::counting_iterator<long long>(0),
-                                                           SideFlag{cur, seg_lo, side, (long long)n});
-            KD_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_scan, flag_in, flags, 3ll * n, stream));
-            k_scatter<<<grid3, threads, 0, stream>>>(cur, alt, n, seg_lo, seg_mid, side, flags);
-            nl += 5;
-            int *t2 = cur;
-            cur = alt;
-            alt = t2;
-        }
-        if (level0 > 0) {
-            const long long tn = 1ll << level0;
-            k_emit_top<<<(unsigned)((tn + threads - 1) / threads), threads, 0, stream>>>(d_pts, cur, n, level0, axis_at,
-                                                                                         d_nodes);
-            ++nl;
-        }
-        // opt in to > 48 KB of dynamic shared memory (per device; the call is cheap enough to repeat)
-        KD_CHECK(cudaFuncSetAttribute(k_kd_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFinSmemBytes));
-        k_kd_finish<<<1u << level0, kFinThreads, kFinSmemBytes, stream>>>(d_pts, cur, n, level0, split_rule, seg_lo,
-                                                                           d_nodes);
-        ++nl;
-    }
-    KD_CHECK(cudaGetLastError());
-done:
-    cudaFreeAsync(keys, stream);
-    cudaFreeAsync(keys_alt, stream);
-    cudaFreeAsync(flags, stream);
-    cudaFreeAsync(idx0, stream);
-    cudaFreeAsync(lists, stream);
-    cudaFreeAsync(lists_alt, stream);
-    cudaFreeAsync(seg_lo, stream);
-    cudaFreeAsync(seg_mid, stream);
-    cudaFreeAsync(side, stream);
-    cudaFreeAsync(axis_at, stream);
-    cudaFreeAsync(tmp, stream);
-    if (launches) *launches += nl;
-    return status;
-}
 
 // ------------------------------------------------------------------------------ query ------
 __device__ __forceinline__ void load_node(const KdNode *__restrict__ nodes, int i, double &x, double &y,
@@ -516,33 +63,6 @@ __device__ __forceinline__ void scan_run(const KdNode *__restrict__ nodes, int l
             best = d;
             bidx = idx;
         }
-    }
-}
-
-// Morton (Z-order) keys of the queries, 10 bits per axis inside the tree's bounding box: sorting
-// the queries by this key makes the 32 lanes of a warp walk nearly the same root-to-leaf paths
-// (coherent branches, shared cache lines).  Ordering only affects speed, never the answers.
-__device__ __forceinline__ unsigned spread10(unsigned v) {
-    v &= 0x3ffu;
-    v = (v | (v << 16)) & 0x030000ffu;
-    v = (v | (v << 8)) & 0x0300f00fu;
-    v = (v | (v << 4)) & 0x030c30c3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
-__global__ void k_morton_keys(const double *__restrict__ queries, long long nq, const double *__restrict__ bbox,
-                              unsigned *__restrict__ keys, int *__restrict__ vals) {
-    const double lo0 = bbox[0], lo1 = bbox[1], lo2 = bbox[2];
-    const double s0 = 1023.0 / fmax(bbox[3] - lo0, 1e-300), s1 = 1023.0 / fmax(bbox[4] - lo1, 1e-300),
-                 s2 = 1023.0 / fmax(bbox[5] - lo2, 1e-300);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nq;
-         i += (long long)gridDim.x * blockDim.x) {
-        const double x = (queries[i * 3] - lo0) * s0, y = (queries[i * 3 + 1] - lo1) * s1,
-                     z = (queries[i * 3 + 2] - lo2) * s2;
-        const unsigned ix = (unsigned)fmin(fmax(x, 0.0), 1023.0), iy = (unsigned)fmin(fmax(y, 0.0), 1023.0),
-                       iz = (unsigned)fmin(fmax(z, 0.0), 1023.0);  // NaN -> 0
-        keys[i] = spread10(ix) | (spread10(iy) << 1) | (spread10(iz) << 2);
-        vals[i] = (int)i;
     }
 }
 
@@ -828,11 +348,8 @@ cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const d
     if (nq == 0) return cudaSuccess;
     const int threads = 128;
     const unsigned grid = (unsigned)((nq + threads - 1) / threads);
-    // Measured on B200 (profiles/README.md): Morton-ordering the queries speeds the traversal itself up
-    // by only 13 % (1 M points, 131 072 queries: 127.6 -> 111.2 us) while key generation + radix sort
-    // cost ~75 us, so it is off unless NAV_KD_SORT=1 (e.g. for much larger query sets).
-    static const int sort_mode = getenv("NAV_KD_SORT") ? atoi(getenv("NAV_KD_SORT")) : 0;
-    const bool sort_queries = sort_mode && d_bbox && n >= 4096 && nq >= 8192 && nq < (size_t)0x7fffffff;
+    // (Ordering the queries along a Morton curve was measured in round 1: 13 % off the traversal, 75 us of
+    // sorting in front of it -- dropped, together with the library sort it needed; profiles/README.md.)
     // Kernel choice by measurement on B200 (131 072 queries, widest-extent trees, 8-node runs scanned;
     // profiles/README.md), short stack / plain stackless / converged stackless:
     //   1 M uniform points 80 / 96 / 108 us, 4 M 124 / 126 / 144 us, 10 M 164 / 178 / 171 us,
@@ -842,7 +359,7 @@ cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const d
     static const char *kk = getenv("NAV_KD_KERNEL");  // read once
     const bool use_stack = kk ? !strcmp(kk, "stack") : true;
     const bool use_conv = kk && !strcmp(kk, "conv");
-    if (!sort_queries && use_conv && d_counter && n > 0) {
+    if (use_conv && d_counter && n > 0) {
         cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream);
         unsigned pgrid = (unsigned)sm_count * 12u;  // 12 x 128 threads = 48 warps per SM (40 registers)
         if ((unsigned long long)pgrid * threads > nq) pgrid = (unsigned)((nq + threads - 1) / threads);
@@ -851,42 +368,12 @@ cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const d
         if (launches) *launches += 1;
         return cudaGetLastError();
     }
-    if (!sort_queries) {
-        if (use_stack)
-            k_kd_nn_stack<<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx,
-                                                        d_dist);
-        else
-            k_kd_nn<<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx, d_dist);
-        if (launches) *launches += 1;
-        return cudaGetLastError();
-    }
-    cudaError_t status = cudaSuccess;
-    unsigned *keys = nullptr, *keys_out = nullptr;
-    int *vals = nullptr, *perm = nullptr;
-    void *tmp = nullptr;
-    size_t tmp_bytes = 0;
-    KD_CHECK(cudaMallocAsync(&keys, nq * 4, stream));
-    KD_CHECK(cudaMallocAsync(&keys_out, nq * 4, stream));
-    KD_CHECK(cudaMallocAsync(&vals, nq * 4, stream));
-    KD_CHECK(cudaMallocAsync(&perm, nq * 4, stream));
-    KD_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_out, vals, perm, (int)nq, 0, 30, stream));
-    KD_CHECK(cudaMallocAsync(&tmp, tmp_bytes, stream));
-    {
-        int kgrid = (int)((nq + 255) / 256);
-        if (kgrid > sm_count * 8) kgrid = sm_count * 8;
-        k_morton_keys<<<kgrid, 256, 0, stream>>>(d_queries, (long long)nq, d_bbox, keys, vals);
-    }
-    KD_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_out, vals, perm, (int)nq, 0, 30, stream));
-    k_kd_nn<<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, perm, d_idx, d_dist);
-    if (launches) *launches += 6;
-    KD_CHECK(cudaGetLastError());
-done:
-    cudaFreeAsync(keys, stream);
-    cudaFreeAsync(keys_out, stream);
-    cudaFreeAsync(vals, stream);
-    cudaFreeAsync(perm, stream);
-    cudaFreeAsync(tmp, stream);
-    return status;
+    if (use_stack)
+        k_kd_nn_stack<<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx, d_dist);
+    else
+        k_kd_nn<<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx, d_dist);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
 }
 
 // --------------------------------------------------------------- exact fp64 brute force ------

@@ -14,6 +14,8 @@ static_assert(sizeof(KdNode) == 32, "one DRAM sector per node");
 enum { kSplitCyclic = 0, kSplitWidest = 1 };  // = NAV_KD_SPLIT_* of include/navslam_b200.h
 cudaError_t kd_build(const double *d_pts, size_t n, KdNode *d_nodes, double *d_bbox, int sm_count,
                      cudaStream_t stream, uint64_t *launches, int split_rule);
+// stream-ordered allocation from the library's own memory pool of `device` (freed with cudaFreeAsync)
+cudaError_t kd_pool_alloc(void **p, size_t bytes, int device, cudaStream_t stream);
 cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const double *d_queries, size_t nq,
                   int *d_idx, double *d_dist, int sm_count, cudaStream_t stream, uint64_t *launches,
                   unsigned long long *d_counter);  // d_counter: 8 bytes of device scratch (work queue head)

@@ -45,6 +45,44 @@ static struct {
 } g_slots[MAX_ATTRS];
 static nav_ctx *g_default_ctx;
 
+/* The reference's callers keep their clouds in ordinary (pageable) memory -- one PointCloud on the stack of
+ * the L5 handler (src/main.c:250), ten in the L9 handler (src/main.c:363), the SLAM_attr with its hundred
+ * global clouds (src/main.c:252,381).  Copying 3 MB frames through a bounce buffer costs more than the GPU
+ * work, so with NAVSLAM_PIN=1 the shim page-locks those buffers where they lie the first time it sees them;
+ * a failed registration just leaves the buffer on the staged path.  Opt-in, because the reference's
+ * interface has no teardown call: a registration is keyed by address, so it is only safe for buffers that
+ * live as long as the program does (which is how main.c holds them) -- a caller that frees a cloud and
+ * gets the same address back from malloc would DMA into the pages of the old mapping. */
+#define MAX_PINNED 16
+static const void *g_pinned[MAX_PINNED];
+static unsigned g_pin_next;
+
+static int pin_enabled(void) {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("NAVSLAM_PIN");
+        v = e && e[0] == '1';
+    }
+    return v;
+}
+
+static void pin_buffer(const void *p, size_t bytes) {
+    if (!pin_enabled() || bytes < (1u << 16)) return; /* small frames are not worth a registration */
+    for (int i = 0; i < MAX_PINNED; ++i)
+        if (g_pinned[i] == p) return;
+    unsigned slot = g_pin_next++ % MAX_PINNED;
+    if (g_pinned[slot]) nav_host_unregister((void *)g_pinned[slot]);
+    g_pinned[slot] = nav_host_register((void *)p, bytes) == 0 ? p : NULL;
+}
+
+static void unpin_buffer(const void *p) {
+    for (int i = 0; i < MAX_PINNED; ++i)
+        if (g_pinned[i] == p && p) {
+            nav_host_unregister((void *)p);
+            g_pinned[i] = NULL;
+        }
+}
+
 static void die(const char *what) {
     fprintf(stderr, "navslam_shim(%dx%d): %s: %s\n", MAX_ROWS, MAX_COLS, what, nav_last_error());
     abort();
@@ -101,6 +139,7 @@ struct nav_ctx *navslam_context_of(SLAM_attr *attr) {
 void navslam_release(SLAM_attr *attr) {
     int s = slot_of(attr, 0);
     if (s < 0) return;
+    unpin_buffer(attr);
     nav_destroy(g_slots[s].ctx);
     memset(&g_slots[s], 0, sizeof(g_slots[s]));
 }
@@ -108,6 +147,8 @@ void navslam_release(SLAM_attr *attr) {
 static void release_all(void) {
     for (int i = 0; i < MAX_ATTRS; ++i)
         if (g_slots[i].attr) navslam_release(g_slots[i].attr);
+    for (int i = 0; i < MAX_PINNED; ++i)
+        if (g_pinned[i]) unpin_buffer(g_pinned[i]);
     if (g_default_ctx) nav_destroy(g_default_ctx);
     g_default_ctx = NULL;
 }
@@ -131,6 +172,8 @@ size_t navslam_abi_offsetof_error(void) { return offsetof(SLAM_attr, error); }
 /* headers/slam.h:22, src/slam.c:134-175 */
 void init_slam(SLAM_attr *attr, Pos pos, PointCloud *lidarPointCloud) {
     int s = slot_of(attr, 1);
+    pin_buffer(attr, sizeof(SLAM_attr));
+    pin_buffer(lidarPointCloud, sizeof(PointCloud));
     attr->frameCount = 0;
     attr->error = 0.0;
     attr->globalPointCloud[0].ToF_timestamps = lidarPointCloud->ToF_timestamps;
@@ -151,6 +194,7 @@ Pos slam_localization(SLAM_attr *attr, PointCloud *lidarPointCloud, Pos pos_pred
     }
     Pos out;
     double err = 0.0;
+    pin_buffer(lidarPointCloud, sizeof(PointCloud));
     /* default: the reference's sequential Adam loop on the host (bit-identical poses and the same
      * per-iteration stdout).  NAVSLAM_ADAM=stats: fit from five device-reduced sums (no 3.5 MB
      * correspondence download, no 200 x N host loop; poses equal to ~1e-9 relative, no per-iteration
@@ -193,6 +237,7 @@ void slam_mapping(SLAM_attr *attr, Pos pos, PointCloud *lidarPointCloud) {
      * re-runs extract_feature (src/slam.c:420).  NAVSLAM_TRUST_FRAME=1 lets the shim reuse the
      * device-resident cloud + labels when the same buffer was just localised. */
     const nav_point *cloud = (const nav_point *)&lidarPointCloud->ToF_position[0][0];
+    pin_buffer(lidarPointCloud, sizeof(PointCloud));
     static int trust = -1;
     if (trust < 0) {
         const char *e = getenv("NAVSLAM_TRUST_FRAME");

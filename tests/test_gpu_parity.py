@@ -372,11 +372,26 @@ def _check_inorder(nodes, axes, lo, hi, depth, split):
 
 
 @pytest.mark.parametrize("split", ["widest", "cyclic"])
-@pytest.mark.parametrize("kind", ["uniform", "clustered", "integer", "duplicates", "sorted", "all_equal", "planes"])
-@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 1000, 2049, 4096, 30000])
+@pytest.mark.parametrize("kind", ["uniform", "clustered", "integer", "duplicates", "sorted", "all_equal", "planes",
+                                  "tight_cluster", "integer_walls"])
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 17, 1000, 2049, 4096, 30000, 70001])
 def test_kdtree_exact_lowest_index(pkg, oracle, synth, kind, n, split):
     rng = np.random.default_rng(n + 13)
-    if kind == "uniform":
+    if kind == "tight_cluster":
+        # nearly all keys inside one histogram bin of the first selection round (a few far outliers stretch the
+        # box): the candidates do not fit in shared memory and the range is narrowed on the lower key bits
+        pts = 1.0e6 + rng.uniform(0.0, 1.0e-3, size=(n, 3))
+        if n >= 17:
+            pts[rng.integers(0, n, 10)] = rng.uniform(-1.0e9, 1.0e9, size=(10, 3))
+    elif kind == "integer_walls":
+        # integer millimetres with two thirds of the points on walls (one coordinate equal for thousands of
+        # points): equal keys beyond the shared-memory capacity, resolved on the point index
+        pts = np.rint(rng.uniform(-8000, 8000, size=(n, 3)))
+        if n:
+            wall = rng.random(n) < 0.67
+            ax = rng.integers(0, 2, n)
+            pts[np.arange(n)[wall], ax[wall]] = rng.choice([-8000.0, 8000.0], int(wall.sum()))
+    elif kind == "uniform":
         pts = synth.map_points(n, seed=n)
     elif kind == "clustered":
         pts = synth.map_points(n, variant="clustered", seed=n)
