@@ -671,11 +671,37 @@ def run_gpu_arm(args):
                 "pose_error_mm": float(np.abs(state["last"][:3] - pose_of(cur)[:3]).max()),
                 "correspondences": int(ncorr.value), "rms_mm": float(err.value)}
 
+    def closed_loop_c(depth=False):
+        """The same loop as ONE C call (nav_slam_run): the prediction is the fitted pose plus a dead-reckoning
+        increment per frame, the host loop is the library's, not Python's."""
+        n_steps = max(K, 400)
+        idx = [triangle(i, n_res) for i in range(0, W + n_steps + 1)]
+        bias = np.array([-2.0, 0.5, 0.0, 0.0, 0.0, 0.0])
+        deltas = np.stack([pose_of(idx[i]) - pose_of(idx[i - 1]) + bias for i in range(1, len(idx))])
+        ptrs = [(h_depth.data_ptr() + (j % n_depth) * NPX * 4) if depth else (h_base + j * FRAME_BYTES) for j in idx[1:]]
+        spin_up()
+        ctx.slam_init(pose_of(0), frames[0], want_global=False)
+        poses, _, _ = ctx.slam_run(ptrs[:W], deltas[:W], pose_of(0), depth_input=depth)
+        ctx.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        poses, errs, ncs = ctx.slam_run(ptrs[W:], deltas[W:], poses[-1], depth_input=depth)
+        ctx.synchronize()
+        barrier()
+        wall = reduce_max([time.perf_counter() - t0])[0]
+        return {"us_per_frame": 1e6 * wall / n_steps, "frames_per_s": world * n_steps / wall, "steps_timed": n_steps,
+                "api": "nav_slam_run (one C call for the whole timed sequence; upload + labels of frame t+1 under the "
+                       "match, fit and mapping of frame t)",
+                "h2d_bytes_per_step": NPX * (4 if depth else 24), "d2h_bytes_per_step": 48,
+                "pose_error_mm": float(np.abs(poses[-1][:3] - pose_of(idx[-1])[:3]).max()),
+                "correspondences": int(ncs[-1]), "rms_mm": float(errs[-1])}
+
     closed = None
     if not args.skip_closed_loop:
         try:
-            closed = {"prefetch": closed_loop(True), "blocking": closed_loop(False)}
+            closed = {"c_loop": closed_loop_c(), "prefetch": closed_loop(True), "blocking": closed_loop(False)}
             if not args.skip_depth_loop:
+                closed["c_loop_depth_input"] = closed_loop_c(depth=True)
                 closed["prefetch_depth_input"] = closed_loop(True, depth=True)
         except Exception as ex:  # noqa: BLE001
             closed = {"error": str(ex)[:300]}

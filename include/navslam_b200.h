@@ -198,7 +198,7 @@ int nav_frontend_frame_depth_async(nav_ctx *ctx, const int *distances, const nav
  * nav_slam_prefetch queues both on a copy stream and returns at once; a later
  * nav_slam_localization_fast(ctx, cloud, ...) with the same `cloud` pointer (or NULL = the oldest prefetched
  * frame) finds the frame resident and labelled and only runs match + dedupe + statistics (2.5 KB come back).
- * nav_slam_mapping(ctx, pos, NULL, NULL) then maps that frame without synchronising.  Up to two frames may
+ * nav_slam_mapping(ctx, pos, NULL, NULL) then maps that frame without synchronising.  Up to three frames may
  * be prefetched ahead.  The host buffer must be pinned and stay untouched until the localization call
  * that consumes it returns.
  *     nav_slam_prefetch(ctx, frame[1]);
@@ -212,6 +212,17 @@ int nav_slam_prefetch(nav_ctx *ctx, const nav_point *cloud);
 /* the same for L5 input: uploads the depth matrix and converts it on the device; consume it with
  * nav_slam_localization_fast(ctx, NULL, ...) */
 int nav_slam_prefetch_depth(nav_ctx *ctx, const int *distances);
+/* The loop above as one call (src/main.c:300-318 with the EKF's prediction supplied by the caller): for
+ * t = 0 .. n_frames-1: pred = predict(user, t, &last) -- or last + deltas[t] when predict is NULL --,
+ * poses_out[t] = nav_slam_localization_fast(frames[t], pred, last), nav_slam_mapping(poses_out[t]),
+ * last = poses_out[t]; `last` starts as *pos_start (the pose nav_slam_init mapped frame -1 with).
+ * frames[t]: pinned nav_point[rows*cols] clouds, or pinned int[rows*cols] depth matrices when depth_input != 0.
+ * error_out / n_corr_out: optional per-frame RMS residual and correspondence count.  Same poses as the
+ * separate calls. */
+typedef void (*nav_predict_fn)(void *user, int t, const nav_pos *last, nav_pos *pred_out);
+int nav_slam_run(nav_ctx *ctx, const void *const *frames, int n_frames, int depth_input, nav_predict_fn predict,
+                 void *user, const nav_pos *deltas, const nav_pos *pos_start, nav_pos *poses_out, double *error_out,
+                 size_t *n_corr_out);
 
 /* ---- data formats either side of the path (host code) ----------------- */
 /* replaces L9_LidarProcessData (src/main.c:77-128): parses "frame,row,col,x,y,z,conf" records after one

@@ -54,7 +54,7 @@ EXPORTS = [
     "nav_l9_csv_read", "nav_csv_header", "nav_csv_format_frame", "nav_csv_format_frame_gpu",
     "nav_csv_format_frame_dev", "nav_l5_json_read", "nav_imu_json_read",
     "nav_frontend_submit", "nav_frontend_frame_depth_async", "nav_slam_prefetch", "nav_slam_prefetch_depth",
-    "nav_host_register", "nav_host_unregister",
+    "nav_host_register", "nav_host_unregister", "nav_slam_run",
 ]
 
 
@@ -128,6 +128,8 @@ def load_library(build_if_missing: bool = True):
                                       C.POINTER(NavPos)]
     L.nav_frontend_frame_depth_async.argtypes = [vp, vp, C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(NavPos),
                                                  vp, vp, vp, vp, vp]
+    L.nav_slam_run.argtypes = [vp, C.POINTER(C.c_void_p), C.c_int, C.c_int, vp, vp, C.POINTER(NavPos),
+                               C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(C.c_double), C.POINTER(C.c_size_t)]
     L.nav_slam_prefetch.argtypes = [vp, vp]
     L.nav_slam_prefetch_depth.argtypes = [vp, vp]
     L.nav_l9_csv_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_size_t, vp, vp, C.POINTER(C.c_size_t)]
@@ -359,6 +361,20 @@ class Context:
         _check(self.L.nav_slam_localization_fast(self.h, cloud_ptr, _pos_array(pos_predict), _pos_array(pos_last),
                                                  C.byref(out), C.byref(err), C.byref(n)), self.L)
         return np.array([out.x, out.y, out.z, out.roll, out.pitch, out.yaw]), err.value, int(n.value)
+
+    def slam_run(self, frame_ptrs, deltas, pos_start, depth_input=False):
+        """nav_slam_run: the closed loop over pinned host frames (raw pointers) with dead-reckoning increments
+        deltas[t] (prediction = last pose + deltas[t]).  Returns (poses [n,6], rms [n], n_corr [n])."""
+        n = len(frame_ptrs)
+        ptrs = (C.c_void_p * n)(*[int(p) for p in frame_ptrs])
+        d = (NavPos * n)(*[NavPos(*[float(v) for v in row]) for row in np.asarray(deltas, dtype=np.float64).reshape(n, 6)])
+        out = (NavPos * n)()
+        err = (C.c_double * n)()
+        nc = (C.c_size_t * n)()
+        _check(self.L.nav_slam_run(self.h, ptrs, n, 1 if depth_input else 0, None, None, d, _pos_array(pos_start),
+                                   out, err, nc), self.L)
+        poses = np.array([[p.x, p.y, p.z, p.roll, p.pitch, p.yaw] for p in out]).reshape(n, 6)
+        return poses, np.array(err[:]), np.array(nc[:], dtype=np.int64)
 
     def frontend_wait(self):
         _check(self.L.nav_frontend_wait(self.h), self.L)

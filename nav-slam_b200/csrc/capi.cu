@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 #include <string.h>
 
 #include <string>
@@ -239,13 +240,24 @@ struct nav_ctx {
         cudaEvent_t ready = nullptr, released = nullptr;
         const void *host_src = nullptr;  // identity of the prefetched frame
         bool pending = false;
-    } pre[2];
+        bool release_recorded = false;   // `released` already marks the end of the slot's last reader
+    } pre[3];
     int pre_next = 0;
+    PreSlot *cur_pre = nullptr;  // the prefetched slot the last localization call consumed
     // the frame the last localization call worked on (mapping with cloud == NULL maps this one)
     const double *cur_cloud = nullptr;
     int *cur_labels = nullptr;
     double *d_row_stats = nullptr;  // [n_seq*rows][5] per-row sufficient statistics of the translation fit
-    double *h_row_stats = nullptr;  // pinned copy
+    double *d_tile_stats = nullptr; // [n_seq*rows*tiles][5] per-tile partial sums (k_dedupe_stats)
+    // closed loop: the dedupe kernel posts the frame's five totals + a sequence number here (host-mapped,
+    // polled by nav_slam_localization_fast instead of a copy + stream synchronisation)
+    double *h_fit = nullptr;
+    unsigned *d_fit_ticket = nullptr;
+    unsigned long long fit_seq = 0;
+    // NAV_RUN_TRACE=1: nav_slam_run prints where the host side of the closed loop spends its time
+    // [prefetch call, launches of match + dedupe, wait for the statistics, fit, mapping call]
+    bool trace = false;
+    double trace_us[5] = {0, 0, 0, 0, 0};
     bool prof = false;
     ProfSlot prof_labels, prof_match, prof_map;
 };
@@ -339,7 +351,9 @@ extern "C" void nav_destroy(nav_ctx *c) {
             if (e) cudaEventDestroy(e);
     }
     if (c->d_row_stats) cudaFree(c->d_row_stats);
-    if (c->h_row_stats) cudaFreeHost(c->h_row_stats);
+    if (c->d_tile_stats) cudaFree(c->d_tile_stats);
+    if (c->h_fit) cudaFreeHost(c->h_fit);
+    if (c->d_fit_ticket) cudaFree(c->d_fit_ticket);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     c->stage.release();
@@ -407,6 +421,7 @@ extern "C" nav_ctx *nav_create(int rows, int cols, int device, int n_seq) {
     ALLOC(c->d_n_exact, 4);
     ALLOC(c->d_stats, (size_t)n_seq * 5 * 8);
     ALLOC(c->d_row_stats, nr * 5 * 8);
+    ALLOC(c->d_tile_stats, nr * (size_t)div_up(cols, 256) * 5 * 8);
     ALLOC(c->map.box, nr * c->map.n_chunks * 32);
     ALLOC(c->map.sbox, nr * c->map.n_super * 32);
     c->map_alt.n_chunks = c->map.n_chunks;
@@ -424,11 +439,13 @@ extern "C" nav_ctx *nav_create(int rows, int cols, int device, int n_seq) {
     ALLOC(c->d_tan_row, (size_t)rows * 8);
     ALLOC(c->d_flat, (size_t)cols * 24 * 2 + (size_t)cols * 8);
     ALLOC(c->d_flat_count, 4);
+    ALLOC(c->d_fit_ticket, 4);
 #undef ALLOC
     cudaMemsetAsync(c->map.mask, 0, nr * c->map.n_chunks * 4, c->stream);
     cudaMemsetAsync(c->d_n_exact, 0, 4, c->stream);
+    cudaMemsetAsync(c->d_fit_ticket, 0, 4, c->stream);
     if (cudaHostAlloc((void **)&c->h_small, 4096, cudaHostAllocDefault) != cudaSuccess ||
-        cudaHostAlloc((void **)&c->h_row_stats, nr * 5 * 8, cudaHostAllocDefault) != cudaSuccess) {
+        cudaHostAlloc((void **)&c->h_fit, 64, cudaHostAllocMapped) != cudaSuccess) {
         fail("nav_create: pinned scratch allocation failed");
         nav_destroy(c);
         return nullptr;
@@ -549,7 +566,7 @@ static void run_map(nav_ctx *c, const double *d_cloud, const int *d_labels, cons
 // then the per-row dedupe (a8) producing the correspondence list and/or the per-row fit statistics
 enum { kDedupeNone = 0, kDedupeCorr = 1, kDedupeStats = 2 };
 static void run_match(nav_ctx *c, const double *d_cloud, int *d_labels, bool fused_labels, const PoseBatch &poses,
-                      int dedupe) {
+                      int dedupe, const FitMailbox *mail = nullptr) {
     order_after_async(c);
     MatchOut out = {c->d_nn_idx, c->d_nn_dist, c->d_corr_rows, c->d_corr_row_count};
     {
@@ -565,8 +582,12 @@ static void run_match(nav_ctx *c, const double *d_cloud, int *d_labels, bool fus
                            c->cols, c->stream);
         c->launches += 2;
     } else if (dedupe & kDedupeStats) {
-        launch_dedupe(d_cloud, d_labels, c->map, out, poses, c->n_seq, c->rows, c->cols, c->stream, c->d_row_stats,
-                      false);
+        if (mail && c->n_seq == 1 && dedupe_stats_supported(c->cols))
+            launch_dedupe_stats(d_cloud, d_labels, c->map, out, poses, c->n_seq, c->rows, c->cols, c->stream,
+                                c->d_tile_stats, *mail);
+        else
+            launch_dedupe(d_cloud, d_labels, c->map, out, poses, c->n_seq, c->rows, c->cols, c->stream, c->d_row_stats,
+                          false, mail);
         c->launches += 1;
     }
 }
@@ -822,10 +843,12 @@ static int prefetch_common(nav_ctx *c, const char *name, const nav_point *cloud,
     if (!Stager::is_pinned(src)) return fail("%s: the host buffer must be pinned (nav_host_alloc / cudaHostRegister)", name);
     if (pre_setup(c)) return 1;
     nav_ctx::PreSlot &ps = c->pre[c->pre_next];
-    if (ps.pending) return fail("%s: two prefetched frames are already waiting for nav_slam_localization_fast", name);
+    if (ps.pending) return fail("%s: three prefetched frames are already waiting for nav_slam_localization_fast", name);
     // the slot's buffers were last used by the frame before the current one: its map kernel is the last
-    // reader and is already queued on the context's stream
-    CU(cudaEventRecord(ps.released, c->stream));
+    // reader and is already queued on the context's stream (nav_slam_run records the event right behind that
+    // kernel, so that a prefetch issued later -- under the next frame's match -- does not wait for more)
+    if (!ps.release_recorded) CU(cudaEventRecord(ps.released, c->stream));
+    ps.release_recorded = false;
     CU(cudaStreamWaitEvent(c->s_in, ps.released, 0));
     if (distances) {
         if (!ps.d_depth) CU(cudaMalloc((void **)&ps.d_depth, c->npx * 4));
@@ -841,7 +864,7 @@ static int prefetch_common(nav_ctx *c, const char *name, const nav_point *cloud,
     CU(cudaEventRecord(ps.ready, c->s_in));
     ps.host_src = src;
     ps.pending = true;
-    c->pre_next ^= 1;
+    c->pre_next = (c->pre_next + 1) % 3;
     return 0;
 }
 
@@ -859,58 +882,63 @@ extern "C" int nav_slam_prefetch_depth(nav_ctx *c, const int *distances) {
 // (SURVEY 8f #2): no correspondence list crosses PCIe and the 200 iterations are O(1) each.
 // Same update rule as src/slam.c:341-370; sums are formed in a different order than the
 // reference's sequential loop, so poses agree to rounding (about 1e-9 relative), not bit for bit.
-extern "C" int nav_slam_localization_fast(nav_ctx *c, const nav_point *cloud, const nav_pos *pos_predict,
-                                          const nav_pos *pos_last, nav_pos *pos_out, double *error_out,
-                                          size_t *n_corr_out) {
-    CTX_ENTER(c, "nav_slam_localization_fast");
-    if (!pos_predict || !pos_last || !pos_out) return fail("nav_slam_localization_fast: null argument");
-    if (c->n_seq != 1) return fail("nav_slam_localization_fast: needs n_seq == 1");
-    if (!c->have_map) return fail("nav_slam_localization_fast: call nav_slam_init first");
-    // a prefetched frame?  (cloud == NULL: the oldest one waiting; otherwise the one uploaded from `cloud`)
-    nav_ctx::PreSlot *ps = nullptr;
-    for (int k = 0; k < 2 && !ps; ++k) {
-        nav_ctx::PreSlot &cand = c->pre[(c->pre_next + k) & 1];  // pre_next is the older of two pending slots
-        if (cand.pending && (!cloud || cand.host_src == (const void *)cloud)) ps = &cand;
+//
+// The totals come back through host-mapped memory: the dedupe kernel's last CTA writes them followed by
+// the call's sequence number (FitMailbox), and the host polls that word -- no copy is queued and the
+// stream is not synchronised, which is worth several microseconds of a 60-90 us closed-loop step.
+static double now_us() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
+static int wait_fit_mail(nav_ctx *c, const char *name) {
+    volatile unsigned long long *flag = (volatile unsigned long long *)(c->h_fit + 5);
+    for (unsigned spins = 0; *flag != c->fit_seq; ++spins) {
+        if ((spins & 0x3ffu) == 0x3ffu) {  // every ~1000 polls: has the stream died or drained without posting?
+            const cudaError_t q = cudaStreamQuery(c->stream);
+            if (q != cudaErrorNotReady) {
+                if (q == cudaSuccess && *flag == c->fit_seq) break;
+                cudaGetLastError();
+                return fail("%s: device execution failed: %s", name,
+                            q == cudaSuccess ? "statistics were not posted" : cudaGetErrorString(q));
+            }
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
     }
-    if (!ps && !cloud) return fail("nav_slam_localization_fast: cloud == NULL but no frame has been prefetched");
-    const PoseBatch poses = pose_batch(c, pos_predict, pos_last);
-    if (ps) {
-        CU(cudaStreamWaitEvent(c->stream, ps->ready, 0));
-        run_match(c, ps->d_cloud, ps->d_labels, false, poses, kDedupeStats);
-        ps->pending = false;
-        c->cur_cloud = ps->d_cloud;
-        c->cur_labels = ps->d_labels;
-    } else {
-        if (c->stage.reserve(c->ntot * 24 + 1024, c->stream)) return fail("nav_slam_localization_fast: staging");
-        if (upload_cloud(c, cloud, "nav_slam_localization_fast")) return 1;
-        run_match(c, c->d_cloud, c->d_labels, true, poses, kDedupeStats);
-        c->cur_cloud = c->d_cloud;
-        c->cur_labels = c->d_labels;
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    c->stage.used = 0;  // the upload (if it was staged) has been consumed by the kernels that posted
+    return 0;
+}
+
+// the O(1)-per-iteration Adam loop on the five totals; bias corrections 1 - beta^t from tables computed once
+// with the same pow() calls the loop used to make
+static void fit_from_stats(const double st[5], const nav_pos *pos_predict, const nav_pos *pos_last, nav_pos *pos_out,
+                           double *error_out, size_t *n_corr_out) {
+    static double c1_tab[200], c2_tab[200];
+    static bool have_tab = false;
+    const double lr = 0.1, tol = 1e-6, b1 = 0.9, b2 = 0.999, eps = 1e-8;
+    if (!have_tab) {
+        for (int i = 0; i < 200; ++i) {
+            c1_tab[i] = 1 - pow(b1, i + 1);
+            c2_tab[i] = 1 - pow(b2, i + 1);
+        }
+        __atomic_thread_fence(__ATOMIC_RELEASE);
+        have_tab = true;
     }
-    c->cloud_resident = true;
-    const size_t stats_bytes = (size_t)c->rows * 5 * 8;
-    CU(cudaMemcpyAsync(c->h_row_stats, c->d_row_stats, stats_bytes, cudaMemcpyDeviceToHost, c->stream));
-    if (finish_call(c, "nav_slam_localization_fast")) return 1;
-    double N = 0, S[3] = {0, 0, 0}, Q = 0;
-    for (int r = 0; r < c->rows; ++r) {  // rows in order: the sums are the same bits on every run
-        const double *h = c->h_row_stats + (size_t)r * 5;
-        N += h[0];
-        S[0] += h[1];
-        S[1] += h[2];
-        S[2] += h[3];
-        Q += h[4];
-    }
+    const double N = st[0], S[3] = {st[1], st[2], st[3]}, Q = st[4];
     double t[6] = {pos_predict->x - pos_last->x,       pos_predict->y - pos_last->y,
                    pos_predict->z - pos_last->z,       pos_predict->roll - pos_last->roll,
                    pos_predict->pitch - pos_last->pitch, pos_predict->yaw - pos_last->yaw};
-    const double lr = 0.1, tol = 1e-6, b1 = 0.9, b2 = 0.999, eps = 1e-8;
     double m[3] = {0, 0, 0}, v[3] = {0, 0, 0}, prev = 0, total = 0;
     for (int iter = 0; iter < 200; ++iter) {
         total = Q - 2.0 * (t[0] * S[0] + t[1] * S[1] + t[2] * S[2]) + N * (t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
         if (N == 0) total = 0;
         if (fabs(total - prev) < tol) break;
         prev = total;
-        const double c1 = 1 - pow(b1, iter + 1), c2 = 1 - pow(b2, iter + 1);
+        const double c1 = c1_tab[iter], c2 = c2_tab[iter];
         for (int j = 0; j < 3; ++j) {
             const double g = N > 0 ? -(S[j] - N * t[j]) / N : 0.0;
             m[j] = b1 * m[j] + (1 - b1) * g;
@@ -927,6 +955,167 @@ extern "C" int nav_slam_localization_fast(nav_ctx *c, const nav_point *cloud, co
     pos_out->roll = pos_last->roll + t[3];
     pos_out->pitch = pos_last->pitch + t[4];
     pos_out->yaw = pos_last->yaw + t[5];
+}
+
+// the prefetched frame uploaded from `cloud`, or (cloud == NULL) the oldest one waiting
+static nav_ctx::PreSlot *find_prefetched(nav_ctx *c, const void *cloud) {
+    for (int k = 0; k < 3; ++k) {
+        nav_ctx::PreSlot &cand = c->pre[(c->pre_next + k) % 3];  // pre_next is the slot written longest ago
+        if (cand.pending && (!cloud || cand.host_src == cloud)) return &cand;
+    }
+    return nullptr;
+}
+
+// first half: queue match + dedupe/statistics of the frame (prefetched or uploaded here); nothing is waited for
+static int loc_fast_launch(nav_ctx *c, const nav_point *cloud, const nav_pos *pos_predict, const nav_pos *pos_last) {
+    if (!pos_predict || !pos_last) return fail("nav_slam_localization_fast: null argument");
+    if (c->n_seq != 1) return fail("nav_slam_localization_fast: needs n_seq == 1");
+    if (!c->have_map) return fail("nav_slam_localization_fast: call nav_slam_init first");
+    // a prefetched frame?  (cloud == NULL: the oldest one waiting; otherwise the one uploaded from `cloud`)
+    nav_ctx::PreSlot *ps = find_prefetched(c, cloud);
+    if (!ps && !cloud) return fail("nav_slam_localization_fast: cloud == NULL but no frame has been prefetched");
+    const double t0 = c->trace ? now_us() : 0.0;
+    const PoseBatch poses = pose_batch(c, pos_predict, pos_last);
+    const FitMailbox mail = {c->h_fit, c->d_fit_ticket, ++c->fit_seq};
+    if (ps) {
+        CU(cudaStreamWaitEvent(c->stream, ps->ready, 0));
+        run_match(c, ps->d_cloud, ps->d_labels, false, poses, kDedupeStats, &mail);
+        ps->pending = false;
+        c->cur_pre = ps;
+        c->cur_cloud = ps->d_cloud;
+        c->cur_labels = ps->d_labels;
+    } else {
+        c->cur_pre = nullptr;
+        if (c->stage.reserve(c->ntot * 24 + 1024, c->stream)) return fail("nav_slam_localization_fast: staging");
+        if (upload_cloud(c, cloud, "nav_slam_localization_fast")) return 1;
+        run_match(c, c->d_cloud, c->d_labels, true, poses, kDedupeStats, &mail);
+        c->cur_cloud = c->d_cloud;
+        c->cur_labels = c->d_labels;
+    }
+    c->cloud_resident = true;
+    CU(cudaGetLastError());
+    if (c->trace) c->trace_us[1] += now_us() - t0;
+    return 0;
+}
+
+// second half: wait for the statistics and fit
+static int loc_fast_finish(nav_ctx *c, const nav_pos *pos_predict, const nav_pos *pos_last, nav_pos *pos_out,
+                           double *error_out, size_t *n_corr_out) {
+    if (!pos_out) return fail("nav_slam_localization_fast: null argument");
+    const double t1 = c->trace ? now_us() : 0.0;
+    if (wait_fit_mail(c, "nav_slam_localization_fast")) return 1;
+    const double t2 = c->trace ? now_us() : 0.0;
+    fit_from_stats(c->h_fit, pos_predict, pos_last, pos_out, error_out, n_corr_out);
+    if (c->trace) {
+        c->trace_us[2] += t2 - t1;
+        c->trace_us[3] += now_us() - t2;
+    }
+    return 0;
+}
+
+extern "C" int nav_slam_localization_fast(nav_ctx *c, const nav_point *cloud, const nav_pos *pos_predict,
+                                          const nav_pos *pos_last, nav_pos *pos_out, double *error_out,
+                                          size_t *n_corr_out) {
+    CTX_ENTER(c, "nav_slam_localization_fast");
+    if (!pos_out) return fail("nav_slam_localization_fast: null argument");
+    if (loc_fast_launch(c, cloud, pos_predict, pos_last)) return 1;
+    return loc_fast_finish(c, pos_predict, pos_last, pos_out, error_out, n_corr_out);
+}
+
+// The closed loop of a whole sequence in one call: the loop of src/main.c:300-318 with the EKF prediction
+// supplied by the caller -- a callback, or an array of dead-reckoning increments (pred = last + delta[t]).
+// Frame t+1 is prefetched (upload + labels on the copy-in stream) while frame t is matched and fitted.
+extern "C" int nav_slam_run(nav_ctx *c, const void *const *frames, int n_frames, int depth_input,
+                            nav_predict_fn predict, void *user, const nav_pos *deltas, const nav_pos *pos_start,
+                            nav_pos *poses_out, double *error_out, size_t *n_corr_out) {
+    CTX_ENTER(c, "nav_slam_run");
+    if (!frames || n_frames < 0 || !pos_start || !poses_out || (!predict && !deltas))
+        return fail("nav_slam_run: null argument");
+    if (c->n_seq != 1) return fail("nav_slam_run: needs n_seq == 1");
+    if (!c->have_map) return fail("nav_slam_run: call nav_slam_init first");
+    nav_pos last = *pos_start;
+    auto prefetch = [&](int t) {
+        return depth_input ? prefetch_common(c, "nav_slam_run", nullptr, (const int *)frames[t])
+                           : prefetch_common(c, "nav_slam_run", (const nav_point *)frames[t], nullptr);
+    };
+    for (auto &ps : c->pre) ps.pending = false;
+    // NAV_RUN_UNFUSED=1 keeps the three launches per frame (match, statistics dedupe, map) of the separate calls
+    static const bool unfused = getenv("NAV_RUN_UNFUSED") != nullptr;
+    const bool fused = !unfused && dedupe_stats_supported(c->cols);
+    nav_ctx::PreSlot *deferred = nullptr;  // fused: the frame whose map the next launch builds first
+    static const bool want_trace = getenv("NAV_RUN_TRACE") != nullptr;
+    c->trace = want_trace;
+    for (double &v : c->trace_us) v = 0.0;
+    if (n_frames > 0 && prefetch(0)) return 1;
+    for (int t = 0; t < n_frames; ++t) {
+        nav_pos pred;
+        if (predict) {
+            predict(user, t, &last, &pred);
+        } else {
+            pred.x = last.x + deltas[t].x;
+            pred.y = last.y + deltas[t].y;
+            pred.z = last.z + deltas[t].z;
+            pred.roll = last.roll + deltas[t].roll;
+            pred.pitch = last.pitch + deltas[t].pitch;
+            pred.yaw = last.yaw + deltas[t].yaw;
+        }
+        double err = 0.0;
+        size_t nc = 0;
+        // queue match + statistics of frame t, THEN the upload + labels of frame t+1 (their API calls cost
+        // host time that is otherwise spent polling), then wait for the statistics and fit
+        if (fused) {
+            // one launch: map of frame t-1 from its fitted pose (deferred from the previous iteration), match of
+            // frame t, statistics dedupe, mailbox post (k_loop_step)
+            const double t0 = c->trace ? now_us() : 0.0;
+            nav_ctx::PreSlot *ps = find_prefetched(c, depth_input ? nullptr : frames[t]);
+            if (!ps) return fail("nav_slam_run: frame %d was not prefetched", t);
+            order_after_async(c);
+            const PoseBatch poses = pose_batch(c, &pred, &last);
+            const PoseBatch prev_poses = pose_batch(c, &last, nullptr);
+            const FitMailbox mail = {c->h_fit, c->d_fit_ticket, ++c->fit_seq};
+            const MatchOut out = {c->d_nn_idx, c->d_nn_dist, c->d_corr_rows, c->d_corr_row_count};
+            CU(cudaStreamWaitEvent(c->stream, ps->ready, 0));
+            CU((cudaError_t)launch_loop_step(ps->d_cloud, ps->d_labels, c->map, out, poses, 1, c->rows, c->cols, c->stream,
+                                             deferred ? deferred->d_cloud : nullptr, deferred ? deferred->d_labels : nullptr,
+                                             prev_poses, deferred != nullptr, c->d_tile_stats, mail));
+            c->launches++;
+            if (deferred) {  // this launch was the last reader of the previous frame's slot
+                CU(cudaEventRecord(deferred->released, c->stream));
+                deferred->release_recorded = true;
+            }
+            ps->pending = false;
+            c->cur_pre = ps;
+            c->cur_cloud = ps->d_cloud;
+            c->cur_labels = ps->d_labels;
+            c->cloud_resident = true;
+            deferred = ps;
+            if (c->trace) c->trace_us[1] += now_us() - t0;
+        } else if (loc_fast_launch(c, depth_input ? nullptr : (const nav_point *)frames[t], &pred, &last)) {
+            return 1;
+        }
+        const double tp = c->trace ? now_us() : 0.0;
+        if (t + 1 < n_frames && prefetch(t + 1)) return 1;
+        if (c->trace) c->trace_us[0] += now_us() - tp;
+        if (loc_fast_finish(c, &pred, &last, &poses_out[t], &err, &nc)) return 1;
+        if (error_out) error_out[t] = err;
+        if (n_corr_out) n_corr_out[t] = nc;
+        const double tm = c->trace ? now_us() : 0.0;
+        if (!fused || t + 1 == n_frames) {  // fused: only the last frame is mapped by a launch of its own
+            if (nav_slam_mapping(c, &poses_out[t], nullptr, nullptr)) return 1;
+            if (c->cur_pre) {  // the map kernel just queued is the last reader of the frame's prefetch slot
+                CU(cudaEventRecord(c->cur_pre->released, c->stream));
+                c->cur_pre->release_recorded = true;
+            }
+        }
+        if (c->trace) c->trace_us[4] += now_us() - tm;
+        last = poses_out[t];
+    }
+    if (c->trace && n_frames > 0) {
+        fprintf(stderr, "nav_slam_run trace, us per frame over %d frames: prefetch call %.2f, match+dedupe launches %.2f, "
+                        "wait for statistics %.2f, fit %.2f, mapping call %.2f\n", n_frames, c->trace_us[0] / n_frames,
+                c->trace_us[1] / n_frames, c->trace_us[2] / n_frames, c->trace_us[3] / n_frames, c->trace_us[4] / n_frames);
+        c->trace = false;
+    }
     return 0;
 }
 

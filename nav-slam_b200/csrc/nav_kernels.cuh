@@ -31,6 +31,14 @@ struct MatchOut {
     int *corr_row_count;  // [n_seq*rows]
 };
 
+// where k_dedupe_rows posts the fit statistics of a whole frame for the host to poll (closed loop):
+// host[0..4] = {N, sum rx, sum ry, sum rz, sum |r|^2}, host[5] = seq (written last, as a 64-bit word)
+struct FitMailbox {
+    double *host;       // host-mapped pinned memory, 6 doubles
+    unsigned *ticket;   // device counter of finished row CTAs (zero between launches)
+    unsigned long long seq;
+};
+
 size_t dedupe_smem_bytes(int cols);
 int configure_row_kernels(int cols);  // opt in to large dynamic shared memory; 0 on success
 
@@ -46,7 +54,18 @@ void launch_frame_match(const double *cloud, int *labels, bool fused_labels, con
 // write_corr = false skips the correspondence entries themselves
 void launch_dedupe(const double *cloud, const int *labels, const RowMap &map, const MatchOut &out,
                    const PoseBatch &poses, int n_seq, int rows, int cols, cudaStream_t stream,
-                   double *row_stats = nullptr, bool write_corr = true);
+                   double *row_stats = nullptr, bool write_corr = true, const FitMailbox *mail = nullptr);
+// statistics-only dedupe spread over the tiles of a row (thread-block cluster per row); part: [n_seq*rows*tiles][5]
+bool dedupe_stats_supported(int cols);
+int launch_dedupe_stats(const double *cloud, const int *labels, const RowMap &map, const MatchOut &out,
+                        const PoseBatch &poses, int n_seq, int rows, int cols, cudaStream_t stream, double *part,
+                        const FitMailbox &mail);
+// the closed-loop step in one launch: (do_map) map of the previous frame from prev_cloud / prev_labels /
+// prev_poses, match of this frame against it, statistics dedupe, mailbox post.  Needs dedupe_stats_supported(cols).
+int launch_loop_step(const double *cloud, const int *labels, const RowMap &map, const MatchOut &out,
+                     const PoseBatch &poses, int n_seq, int rows, int cols, cudaStream_t stream,
+                     const double *prev_cloud, const int *prev_labels, const PoseBatch &prev_poses, bool do_map,
+                     double *part, const FitMailbox &mail);
 void launch_gather_corr(const nav_corr *corr_rows, const int *corr_row_count, nav_corr *corr_out,
                         int *corr_total, int n_seq, int rows, int cols, cudaStream_t stream);
 void launch_corr_stats(const nav_corr *corr, const int *corr_total, double *stats_out, int n_seq, int rows, int cols,

@@ -232,6 +232,148 @@ struct MapSmem {
     unsigned mask[kNbLeaves];
 };
 
+// one row of the map as the search sees it
+struct RowView {
+    const double *pts;
+    const unsigned *mask;
+    const float4 *box;
+    const float4 *sbox;
+    int n_leaf, n_sup, leaf0;  // leaf0: first leaf of the CTA's shared-memory neighbourhood (may be -1)
+};
+
+// map data outside the shared-memory neighbourhood: through the read-only path when the map was written by
+// an earlier launch, with ordinary (coherent) loads when this launch wrote it (k_loop_step)
+template <bool kCoherent, typename T>
+__device__ __forceinline__ T ld_map(const T *p) {
+    if (kCoherent) return *p;
+    return __ldg(p);
+}
+
+// asynchronous prefetch (cp.async) of a CTA's neighbourhood of the row map into shared memory (MapSmem);
+// complete after cp_async_wait_all + a barrier.  Called by all kTile threads.
+template <bool kCoherent>
+__device__ __forceinline__ void prefetch_neighbourhood(MapSmem &sm, const RowView &rv, int cols) {
+    const int leaf0 = rv.leaf0, n_leaf = rv.n_leaf, n_sup = rv.n_sup;
+    const int col_lo = leaf0 * kChunk;
+    for (int i = threadIdx.x; i < kNbLeaves * kChunk * 3; i += kTile) {
+        const int col = col_lo + i / 3;
+        if (col >= 0 && col < cols) cp_async8(&sm.pts[i], rv.pts + (long long)col_lo * 3 + i);
+    }
+    if (threadIdx.x < kNbLeaves * 2) {
+        const int lf = leaf0 + (int)threadIdx.x / 2;
+        if (lf >= 0 && lf < n_leaf) cp_async16(&sm.box[threadIdx.x], rv.box + (long long)leaf0 * 2 + threadIdx.x);
+    } else if (threadIdx.x >= 64 && threadIdx.x < 64 + kNbLeaves) {
+        const int j = threadIdx.x - 64, lf = leaf0 + j;
+        sm.mask[j] = (lf >= 0 && lf < n_leaf) ? ld_map<kCoherent>(rv.mask + lf) : 0u;
+    } else if (threadIdx.x >= 128 && (int)threadIdx.x < 128 + 2 * min(n_sup, kMaxSuperSmem)) {
+        cp_async16(&sm.sbox[threadIdx.x - 128], rv.sbox + (threadIdx.x - 128));
+    }
+    // every leaf box of the row: a query near the edge of its tile (or far from its neighbour) tests
+    // the leaves of other super blocks too, and sixteen dependent global loads made those warps the tail
+    if (n_leaf <= kMaxRowLeafSmem && (int)threadIdx.x < 2 * n_leaf) cp_async16(&sm.rbox[threadIdx.x], rv.box + threadIdx.x);
+}
+
+// exact nearest labelled map point of the row for query q of column qc: seed leaf, its neighbours, then the
+// box hierarchy.  best = smallest dsq (INFINITY if the row map is empty), bcol = its column (lowest on ties).
+template <bool kCoherent>
+__device__ __forceinline__ void search_row(const MapSmem &sm, const RowView &rv, int qc, const P3 &q, double &best,
+                                           int &bcol) {
+    const double *m_pts = rv.pts;
+    const unsigned *m_mask = rv.mask;
+    const float4 *m_box = rv.box, *m_sbox = rv.sbox;
+    const int n_leaf = rv.n_leaf, n_sup = rv.n_sup, leaf0 = rv.leaf0;
+    const Q32 q32 = make_q32(q);
+    const bool sup_in_smem = n_sup <= kMaxSuperSmem, row_in_smem = n_leaf <= kMaxRowLeafSmem;
+
+    best = INFINITY;
+    float best_up = INFINITY;  // float(best) rounded up
+    bcol = -1;
+    const int seed = qc / kChunk;
+    scan_leaf(sm.pts + (seed - leaf0) * kChunk * 3, sm.mask[seed - leaf0], seed * kChunk, q, best, bcol);
+    best_up = __double2float_ru(best);
+    // The leaves next to the seed come first, addressed RELATIVE to the seed: the lanes of a warp hold
+    // queries of neighbouring columns with different seeds, and stepping through "seed-1, seed+1, ..."
+    // together lets every lane scan its own neighbour in the same loop iteration.  (Walking absolute
+    // leaf indices instead made the warp execute the union of all lanes' neighbour scans.)
+    // Measured (64x2048, frames/s single sequence / 8 sequences per launch): kNear 2: 55.3 K / 55.9 K,
+    // kNear 1: 57.8 K / 61.3 K, kNear 0: 49.5 K / 61.0 K -- one neighbour each side gives the mask tests below
+    // a tight bound; a second one is rarely needed and costs two more box tests per query.
+    constexpr int kNear = 1;
+#pragma unroll
+    for (int d = 1; d <= kNear; ++d) {
+#pragma unroll
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+            const int lf = seed + sgn * d, j = lf - leaf0;
+            if (lf < 0 || lf >= n_leaf) continue;
+            const bool near_leaf = j >= 0 && j < kNbLeaves;
+            const float4 blo = row_in_smem ? sm.rbox[lf * 2] : (near_leaf ? sm.box[j * 2] : ld_map<kCoherent>(m_box + lf * 2));
+            const float4 bhi = row_in_smem ? sm.rbox[lf * 2 + 1] : (near_leaf ? sm.box[j * 2 + 1] : ld_map<kCoherent>(m_box + lf * 2 + 1));
+            if (box_lower_bound32(blo, bhi, q32) > best_up) continue;
+            if (near_leaf)
+                scan_leaf(sm.pts + j * kChunk * 3, sm.mask[j], lf * kChunk, q, best, bcol);
+            else
+                scan_leaf(m_pts + (long long)lf * kChunk * 3, ld_map<kCoherent>(m_mask + lf), lf * kChunk, q, best, bcol);
+            best_up = __double2float_ru(best);
+        }
+    }
+    // everything else through the box hierarchy (exactness does not depend on the order of visits)
+    for (int sc = 0; sc < n_sup; ++sc) {
+        const float4 slo = sup_in_smem ? sm.sbox[sc * 2] : ld_map<kCoherent>(m_sbox + sc * 2);
+        const float4 shi = sup_in_smem ? sm.sbox[sc * 2 + 1] : ld_map<kCoherent>(m_sbox + sc * 2 + 1);
+        if (box_lower_bound32(slo, shi, q32) > best_up) continue;
+        const int l1 = min(n_leaf, (sc + 1) * kChunksPerSuper);
+        if (row_in_smem) {
+            // all leaf boxes of the row sit in shared memory: the sixteen lower bounds of a super block are
+            // evaluated as independent chains, four at a time, into a bit mask -- instead of sixteen
+            // dependent test-and-branch rounds -- and only the leaves that pass are visited (and re-tested
+            // against the then-current best)
+            const int l0 = sc * kChunksPerSuper;
+            unsigned pass = 0;
+#pragma unroll
+            for (int g = 0; g < kChunksPerSuper; g += 4) {
+                float lb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int lf = min(l0 + g + i, n_leaf - 1);
+                    lb[i] = box_lower_bound32(sm.rbox[lf * 2], sm.rbox[lf * 2 + 1], q32);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pass |= (unsigned)!(lb[i] > best_up) << (g + i);
+            }
+            // drop the leaves visited above and those beyond the end of the row
+            for (int d = -kNear; d <= kNear; ++d) {
+                const int j = seed + d - l0;
+                if (j >= 0 && j < kChunksPerSuper) pass &= ~(1u << j);
+            }
+            if (l1 - l0 < kChunksPerSuper) pass &= (1u << (l1 - l0)) - 1u;
+            while (pass) {
+                const int lf = l0 + __ffs(pass) - 1, j = lf - leaf0;
+                pass &= pass - 1;
+                if (box_lower_bound32(sm.rbox[lf * 2], sm.rbox[lf * 2 + 1], q32) > best_up) continue;
+                if (j >= 0 && j < kNbLeaves)
+                    scan_leaf(sm.pts + j * kChunk * 3, sm.mask[j], lf * kChunk, q, best, bcol);
+                else
+                    scan_leaf(m_pts + (long long)lf * kChunk * 3, ld_map<kCoherent>(m_mask + lf), lf * kChunk, q, best, bcol);
+                best_up = __double2float_ru(best);
+            }
+            continue;
+        }
+        for (int lf = sc * kChunksPerSuper; lf < l1; ++lf) {
+            if (lf >= seed - kNear && lf <= seed + kNear) continue;  // already visited
+            const int j = lf - leaf0;
+            const bool near_leaf = j >= 0 && j < kNbLeaves;
+            const float4 blo = near_leaf ? sm.box[j * 2] : ld_map<kCoherent>(m_box + lf * 2);
+            const float4 bhi = near_leaf ? sm.box[j * 2 + 1] : ld_map<kCoherent>(m_box + lf * 2 + 1);
+            if (box_lower_bound32(blo, bhi, q32) > best_up) continue;
+            if (near_leaf)
+                scan_leaf(sm.pts + j * kChunk * 3, sm.mask[j], lf * kChunk, q, best, bcol);
+            else
+                scan_leaf(m_pts + (long long)lf * kChunk * 3, ld_map<kCoherent>(m_mask + lf), lf * kChunk, q, best, bcol);
+            best_up = __double2float_ru(best);
+        }
+    }
+}
+
 // grid as k_frame_map.  kFusedLabels: compute the labels of the tile here (and store them);
 // otherwise read them from `labels`.  kFuseMap: also build the NEXT map (this frame transformed with
 // its final pose) into map_next -- a second buffer, because neighbouring CTAs are still searching the
@@ -259,26 +401,9 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
     const float4 *m_sbox = map.sbox + (long long)rid * map.n_super * 2;
     const int n_leaf = map.n_chunks, n_sup = map.n_super;
     const int leaf0 = tile * kChunksPerSuper - 1;  // first leaf of the prefetched neighbourhood (may be -1)
+    const RowView rv = {m_pts, m_mask, m_box, m_sbox, n_leaf, n_sup, leaf0};
     // asynchronous prefetch (cp.async) of the neighbourhood; consumed after the compaction
-    auto prefetch_map = [&]() {
-        const int col_lo = leaf0 * kChunk;
-        for (int i = threadIdx.x; i < kNbLeaves * kChunk * 3; i += kTile) {
-            const int col = col_lo + i / 3;
-            if (col >= 0 && col < cols) cp_async8(&sm.pts[i], m_pts + (long long)col_lo * 3 + i);
-        }
-        if (threadIdx.x < kNbLeaves * 2) {
-            const int lf = leaf0 + (int)threadIdx.x / 2;
-            if (lf >= 0 && lf < n_leaf) cp_async16(&sm.box[threadIdx.x], m_box + (long long)leaf0 * 2 + threadIdx.x);
-        } else if (threadIdx.x >= 64 && threadIdx.x < 64 + kNbLeaves) {
-            const int j = threadIdx.x - 64, lf = leaf0 + j;
-            sm.mask[j] = (lf >= 0 && lf < n_leaf) ? __ldg(m_mask + lf) : 0u;
-        } else if (threadIdx.x >= 128 && (int)threadIdx.x < 128 + 2 * min(n_sup, kMaxSuperSmem)) {
-            cp_async16(&sm.sbox[threadIdx.x - 128], m_sbox + (threadIdx.x - 128));
-        }
-        // every leaf box of the row: a query near the edge of its tile (or far from its neighbour) tests
-        // the leaves of other super blocks too, and sixteen dependent global loads made those warps the tail
-        if (n_leaf <= kMaxRowLeafSmem && (int)threadIdx.x < 2 * n_leaf) cp_async16(&sm.rbox[threadIdx.x], m_box + threadIdx.x);
-    };
+    auto prefetch_map = [&]() { prefetch_neighbourhood<false>(sm, rv, cols); };
     // Programmatic dependent launch (pdl != 0, kernel launched with the stream-serialisation attribute):
     // the next frame's launch may start while this one still runs.  Everything in front of
     // griddepcontrol.wait touches only this frame's own cloud (and shared memory); the previous frame's
@@ -339,96 +464,9 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
     }
     const PoseXf &pose = poses.p[seq];
     const P3 q = shift_point(pose, xf_point(pose, p));
-    const Q32 q32 = make_q32(q);
-    const bool sup_in_smem = n_sup <= kMaxSuperSmem, row_in_smem = n_leaf <= kMaxRowLeafSmem;
-
-    double best = INFINITY;
-    float best_up = INFINITY;  // float(best) rounded up
-    int bcol = -1;
-    const int seed = qc / kChunk;
-    scan_leaf(sm.pts + (seed - leaf0) * kChunk * 3, sm.mask[seed - leaf0], seed * kChunk, q, best, bcol);
-    best_up = __double2float_ru(best);
-    // The leaves next to the seed come first, addressed RELATIVE to the seed: the lanes of a warp hold
-    // queries of neighbouring columns with different seeds, and stepping through "seed-1, seed+1, ..."
-    // together lets every lane scan its own neighbour in the same loop iteration.  (Walking absolute
-    // leaf indices instead made the warp execute the union of all lanes' neighbour scans.)
-    // Measured (64x2048, frames/s single sequence / 8 sequences per launch): kNear 2: 55.3 K / 55.9 K,
-    // kNear 1: 57.8 K / 61.3 K, kNear 0: 49.5 K / 61.0 K -- one neighbour each side gives the mask tests below
-    // a tight bound; a second one is rarely needed and costs two more box tests per query.
-    constexpr int kNear = 1;
-#pragma unroll
-    for (int d = 1; d <= kNear; ++d) {
-#pragma unroll
-        for (int sgn = -1; sgn <= 1; sgn += 2) {
-            const int lf = seed + sgn * d, j = lf - leaf0;
-            if (lf < 0 || lf >= n_leaf) continue;
-            const bool near_leaf = j >= 0 && j < kNbLeaves;
-            const float4 blo = row_in_smem ? sm.rbox[lf * 2] : (near_leaf ? sm.box[j * 2] : __ldg(m_box + lf * 2));
-            const float4 bhi = row_in_smem ? sm.rbox[lf * 2 + 1] : (near_leaf ? sm.box[j * 2 + 1] : __ldg(m_box + lf * 2 + 1));
-            if (box_lower_bound32(blo, bhi, q32) > best_up) continue;
-            if (near_leaf)
-                scan_leaf(sm.pts + j * kChunk * 3, sm.mask[j], lf * kChunk, q, best, bcol);
-            else
-                scan_leaf(m_pts + (long long)lf * kChunk * 3, __ldg(m_mask + lf), lf * kChunk, q, best, bcol);
-            best_up = __double2float_ru(best);
-        }
-    }
-    // everything else through the box hierarchy (exactness does not depend on the order of visits)
-    for (int sc = 0; sc < n_sup; ++sc) {
-        const float4 slo = sup_in_smem ? sm.sbox[sc * 2] : __ldg(m_sbox + sc * 2);
-        const float4 shi = sup_in_smem ? sm.sbox[sc * 2 + 1] : __ldg(m_sbox + sc * 2 + 1);
-        if (box_lower_bound32(slo, shi, q32) > best_up) continue;
-        const int l1 = min(n_leaf, (sc + 1) * kChunksPerSuper);
-        if (row_in_smem) {
-            // all leaf boxes of the row sit in shared memory: the sixteen lower bounds of a super block are
-            // evaluated as independent chains, four at a time, into a bit mask -- instead of sixteen
-            // dependent test-and-branch rounds -- and only the leaves that pass are visited (and re-tested
-            // against the then-current best)
-            const int l0 = sc * kChunksPerSuper;
-            unsigned pass = 0;
-#pragma unroll
-            for (int g = 0; g < kChunksPerSuper; g += 4) {
-                float lb[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int lf = min(l0 + g + i, n_leaf - 1);
-                    lb[i] = box_lower_bound32(sm.rbox[lf * 2], sm.rbox[lf * 2 + 1], q32);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) pass |= (unsigned)!(lb[i] > best_up) << (g + i);
-            }
-            // drop the leaves visited above and those beyond the end of the row
-            for (int d = -kNear; d <= kNear; ++d) {
-                const int j = seed + d - l0;
-                if (j >= 0 && j < kChunksPerSuper) pass &= ~(1u << j);
-            }
-            if (l1 - l0 < kChunksPerSuper) pass &= (1u << (l1 - l0)) - 1u;
-            while (pass) {
-                const int lf = l0 + __ffs(pass) - 1, j = lf - leaf0;
-                pass &= pass - 1;
-                if (box_lower_bound32(sm.rbox[lf * 2], sm.rbox[lf * 2 + 1], q32) > best_up) continue;
-                if (j >= 0 && j < kNbLeaves)
-                    scan_leaf(sm.pts + j * kChunk * 3, sm.mask[j], lf * kChunk, q, best, bcol);
-                else
-                    scan_leaf(m_pts + (long long)lf * kChunk * 3, __ldg(m_mask + lf), lf * kChunk, q, best, bcol);
-                best_up = __double2float_ru(best);
-            }
-            continue;
-        }
-        for (int lf = sc * kChunksPerSuper; lf < l1; ++lf) {
-            if (lf >= seed - kNear && lf <= seed + kNear) continue;  // already visited
-            const int j = lf - leaf0;
-            const bool near_leaf = j >= 0 && j < kNbLeaves;
-            const float4 blo = near_leaf ? sm.box[j * 2] : __ldg(m_box + lf * 2);
-            const float4 bhi = near_leaf ? sm.box[j * 2 + 1] : __ldg(m_box + lf * 2 + 1);
-            if (box_lower_bound32(blo, bhi, q32) > best_up) continue;
-            if (near_leaf)
-                scan_leaf(sm.pts + j * kChunk * 3, sm.mask[j], lf * kChunk, q, best, bcol);
-            else
-                scan_leaf(m_pts + (long long)lf * kChunk * 3, __ldg(m_mask + lf), lf * kChunk, q, best, bcol);
-            best_up = __double2float_ru(best);
-        }
-    }
+    double best;
+    int bcol;
+    search_row<false>(sm, rv, qc, q, best, bcol);
     out.nn_idx[base + qc] = bcol >= 0 ? row * cols + bcol : -1;
     out.nn_dist[base + qc] = bcol >= 0 ? __dsqrt_rn(best) : INFINITY;
 }
@@ -487,6 +525,42 @@ void launch_frame_match(const double *cloud, int *labels, bool fused_labels, con
 
 constexpr int kRowThreads = 512;
 
+// Called by every thread of the CTA that finished last: adds the five partial sums of all `n_part` CTAs
+// (part[i*5 + k]) in a fixed order -- thread-strided with independent loads, a shuffle tree, then warp by
+// warp -- and posts the totals followed by the sequence number to the host mailbox.  T = blockDim.x.
+template <int T>
+__device__ __forceinline__ void post_fit_totals(const double *__restrict__ part, int n_part, const FitMailbox &mail,
+                                                double (*s_tot)[5]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double t[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < n_part; i += T) {
+        double v[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] = __ldcg(part + (long long)i * 5 + k);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) t[k] = dadd(t[k], v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) t[k] = dadd(t[k], __shfl_xor_sync(kFull, t[k], d));
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) s_tot[warp][k] = t[k];
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double a = 0.0;
+        for (int w = 0; w < T / 32; ++w) a = dadd(a, s_tot[w][threadIdx.x]);
+        mail.host[threadIdx.x] = a;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *mail.ticket = 0u;
+        *(volatile unsigned long long *)(mail.host + 5) = mail.seq;
+    }
+}
+
 // per-row dedupe, src/slam.c:247-283: one entry per matched map point; the query with the smallest
 // distance wins (earliest column on equal distance, strict '>' at slam.c:264); entries in order of
 // the first query that matched the point.  One CTA per (sequence,row); dynamic smem = 16 B * cols.
@@ -498,7 +572,7 @@ constexpr int kRowThreads = 512;
 __global__ void __launch_bounds__(kRowThreads)
 k_dedupe_rows(const double *__restrict__ cloud, const int *__restrict__ labels, RowMap map, MatchOut out,
               const __grid_constant__ PoseBatch poses, int rows, int cols, double *__restrict__ row_stats,
-              int write_corr) {
+              int write_corr, FitMailbox mail) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ int s_warp[65];
     __shared__ double s_red[kRowThreads / 32][4];
@@ -585,7 +659,275 @@ k_dedupe_rows(const double *__restrict__ cloud, const int *__restrict__ labels, 
             row_stats[(long long)rid * 5 + 1 + threadIdx.x] = t;
         }
         if (threadIdx.x == 0) row_stats[(long long)rid * 5] = (double)n_out;
+        // mail.host != null (one sequence): the CTA that finishes last adds the rows in row order -- the same
+        // sequential sums the host used to form from the downloaded rows, so the same bits -- and posts the five
+        // totals followed by the call's sequence number into host-mapped memory: the host polls that word
+        // instead of queueing a copy and synchronising the stream
+        if (mail.host) {
+            __shared__ bool s_last;
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) s_last = atomicAdd(mail.ticket, 1u) == gridDim.x - 1;
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                __shared__ double s_tot[kRowThreads / 32][5];
+                post_fit_totals<kRowThreads>(row_stats, (int)gridDim.x, mail, s_tot);
+            }
+        }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same dedupe when only the fit statistics are wanted (closed loop, nav_slam_localization_fast): the
+// order of the entries does not matter, so a row is spread over its tiles -- one CTA per (row, 256-column
+// tile), the CTAs of a row forming a thread-block CLUSTER.  Every CTA owns the "best distance" and
+// "winning column" slots of the 256 map columns of its tile in its shared memory; queries post to the
+// owner's slots through distributed shared memory (a query's neighbour is almost always in its own or the
+// next tile), with cluster barriers between the three phases of src/slam.c:247-283: smallest distance per
+// matched map point, earliest column among those, and the winners' residuals.  512 CTAs instead of 64, one
+// column per thread: 23 us -> a few us per 64x2048 frame.
+// Partial sums: per CTA in a fixed order (shuffle tree, then warp by warp); the CTA that finishes last adds
+// the partials of the whole frame in a fixed order and posts the totals to the host mailbox.
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+
+// Phases 1-3 of the cluster dedupe.  Called by ALL threads of every CTA of the row's cluster (four cluster
+// barriers inside).  key = matched map column of this thread's query (or -1), dbits = bits of its distance,
+// c = the query's column.  Returns whether this query is the one kept for its map point.
+__device__ __forceinline__ bool cluster_dedupe_winner(unsigned long long *s_best, int *s_win, int key,
+                                                      unsigned long long dbits, int c) {
+    s_best[threadIdx.x] = ~0ull;
+    s_win[threadIdx.x] = INT_MAX;
+    unsigned long long *r_best = nullptr;
+    int *r_win = nullptr;
+    if (key >= 0) {  // the slots of map column `key` live in the CTA of its tile (rank = tile index in the cluster)
+        const unsigned owner = (unsigned)(key / kTile);
+        unsigned long long *b0;
+        int *w0;
+        asm("mapa.u64 %0, %1, %2;" : "=l"(b0) : "l"(s_best), "r"(owner));
+        asm("mapa.u64 %0, %1, %2;" : "=l"(w0) : "l"(s_win), "r"(owner));
+        r_best = b0 + key % kTile;
+        r_win = w0 + key % kTile;
+    }
+    cluster_sync_all();  // every CTA of the row has initialised its slots
+    if (key >= 0) atomicMin(r_best, dbits);
+    cluster_sync_all();
+    if (key >= 0 && *(volatile unsigned long long *)r_best == dbits) atomicMin(r_win, c);
+    cluster_sync_all();
+    const bool winner = key >= 0 && *(volatile int *)r_win == c;
+    cluster_sync_all();  // nobody leaves (or reuses its slots) while a neighbour may still read them
+    return winner;
+}
+
+struct StatsSmem {
+    double red[kTile / 32][4];
+    int cnt[kTile / 32];
+    double tot[kTile / 32][5];
+    bool last;
+};
+
+// CTA partial of the fit statistics (r = residual of a winner, zero otherwise) -> part[blockIdx.x][5]; the CTA
+// that finishes last adds the partials of the whole frame and posts them.  Called by all kTile threads.
+__device__ __forceinline__ void block_post_stats(StatsSmem &ss, bool winner, double rx, double ry, double rz,
+                                                 double *__restrict__ part, const FitMailbox &mail) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc[4] = {rx, ry, rz, winner ? dsq3(rx, ry, rz) : 0.0};
+    const int n_w = __popc(__ballot_sync(kFull, winner));
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) acc[k] = dadd(acc[k], __shfl_xor_sync(kFull, acc[k], d));
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ss.red[warp][k] = acc[k];
+        ss.cnt[warp] = n_w;
+    }
+    __syncthreads();
+    double *mine = part + (long long)blockIdx.x * 5;
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < kTile / 32; ++w) t = dadd(t, ss.red[w][threadIdx.x]);
+        mine[1 + threadIdx.x] = t;
+    } else if (threadIdx.x == 4) {
+        int n = 0;
+        for (int w = 0; w < kTile / 32; ++w) n += ss.cnt[w];
+        mine[0] = (double)n;
+    }
+    if (!mail.host) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();  // cumulative: publishes the five stores above (ordered before it by the barrier)
+        ss.last = atomicAdd(mail.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!ss.last) return;
+    __threadfence();
+    post_fit_totals<kTile>(part, (int)gridDim.x, mail, ss.tot);
+}
+
+__global__ void __launch_bounds__(kTile)
+k_dedupe_stats(const double *__restrict__ cloud, const int *__restrict__ labels, RowMap map, MatchOut out,
+               const __grid_constant__ PoseBatch poses, int rows, int cols, int tiles_per_row,
+               double *__restrict__ part, FitMailbox mail) {
+    __shared__ unsigned long long s_best[kTile];
+    __shared__ int s_win[kTile];
+    __shared__ StatsSmem ss;
+    const int rid = blockIdx.x / tiles_per_row, tile = blockIdx.x % tiles_per_row;
+    const int seq = rid / rows, row = rid % rows;
+    const long long base = (long long)rid * cols;
+    const int c = tile * kTile + threadIdx.x;
+    int key = -1;
+    unsigned long long dbits = 0;
+    if (c < cols && labels[base + c] == 1) {
+        const int idx = out.nn_idx[base + c];
+        if (idx >= 0) {
+            key = idx - row * cols;
+            dbits = (unsigned long long)__double_as_longlong(out.nn_dist[base + c]);
+        }
+    }
+    const bool winner = cluster_dedupe_winner(s_best, s_win, key, dbits, c);
+    double rx = 0.0, ry = 0.0, rz = 0.0;
+    if (winner) {
+        const P3 ori = xf_point(poses.p[seq], load_p3(cloud + (base + c) * 3));
+        const double *np = map.pts + (base + key) * 3;
+        rx = dsub(ori.x, np[0]);
+        ry = dsub(ori.y, np[1]);
+        rz = dsub(ori.z, np[2]);
+    }
+    block_post_stats(ss, winner, rx, ry, rz, part, mail);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One launch per frame of the closed loop (nav_slam_run), one thread-block cluster per image row:
+//   1. (do_map) the map of the PREVIOUS frame from its fitted pose (what k_frame_map does), in place --
+//      a row's map is written and searched by the same cluster, a cluster barrier in between;
+//   2. the match of this frame (labels already computed by the prefetch) exactly as k_frame_match;
+//   3. the statistics dedupe of k_dedupe_stats on the results still in registers, and the mailbox post.
+// The serial chain of a frame is then: fit -> this launch -> the host sees the totals.
+__global__ void __launch_bounds__(kTile, NAV_MATCH_MIN_CTAS)
+k_loop_step(const double *__restrict__ cloud, const int *__restrict__ labels, RowMap map, MatchOut out,
+            const __grid_constant__ PoseBatch poses, int rows, int cols, int tiles_per_row,
+            const double *__restrict__ prev_cloud, const int *__restrict__ prev_labels,
+            const __grid_constant__ PoseBatch prev_poses, int do_map, double *__restrict__ part, FitMailbox mail) {
+    __shared__ int s_warp[65];
+    __shared__ int s_qcol[kTile];
+    __shared__ MapSmem sm;
+    __shared__ unsigned long long s_best[kTile];
+    __shared__ int s_win[kTile];
+    __shared__ StatsSmem ss;
+    const int rid = blockIdx.x / tiles_per_row;
+    const int tile = blockIdx.x % tiles_per_row;
+    const int seq = rid / rows, row = rid % rows;
+    const long long base = (long long)rid * cols;
+    const int c0 = tile * kTile;
+    const int c = c0 + threadIdx.x;
+    const int label = c < cols ? labels[base + c] : 0;
+    if (do_map) {
+        __shared__ float4 s_lo[kChunksPerSuper], s_hi[kChunksPerSuper];
+        bool lab = false;
+        P3 p = {0, 0, 0};
+        if (c < cols) {
+            lab = prev_labels[base + c] == 1;
+            p = load_p3(prev_cloud + (base + c) * 3);
+        }
+        map_tile(lab, c < cols, p, prev_poses.p[seq], map, rid, tile, c, base, s_lo, s_hi);
+        cluster_sync_all();  // release / acquire: the row's new map is visible to all CTAs of its cluster
+    }
+    const RowView rv = {map.pts + base * 3, map.mask + (long long)rid * map.n_chunks,
+                        map.box + (long long)rid * map.n_chunks * 2, map.sbox + (long long)rid * map.n_super * 2,
+                        map.n_chunks, map.n_super, tile * kChunksPerSuper - 1};
+    prefetch_neighbourhood<true>(sm, rv, cols);
+    if (c < cols && label != 1) {
+        out.nn_idx[base + c] = -1;
+        out.nn_dist[base + c] = -1.0;
+    }
+    cp_async_wait_all();
+    int nq;
+    const int slot = block_excl_count(label == 1, s_warp, nq);  // its barriers also publish the prefetch
+    if (label == 1) s_qcol[slot] = threadIdx.x;
+    __syncthreads();
+    int key = -1, qc = -1;
+    unsigned long long dbits = 0;
+    P3 ori = {0, 0, 0};
+    if ((int)threadIdx.x < nq) {
+        qc = c0 + s_qcol[threadIdx.x];
+        const PoseXf &pose = poses.p[seq];
+        ori = xf_point(pose, load_p3(cloud + (base + qc) * 3));
+        const P3 q = shift_point(pose, ori);
+        double best;
+        int bcol;
+        search_row<true>(sm, rv, qc, q, best, bcol);
+        const double dist = bcol >= 0 ? __dsqrt_rn(best) : INFINITY;
+        out.nn_idx[base + qc] = bcol >= 0 ? row * cols + bcol : -1;
+        out.nn_dist[base + qc] = dist;
+        if (bcol >= 0) {
+            key = bcol;
+            dbits = (unsigned long long)__double_as_longlong(dist);
+        }
+    }
+    const bool winner = cluster_dedupe_winner(s_best, s_win, key, dbits, qc);
+    // residuals back into COLUMN order (thread = column, as in k_dedupe_stats), so that the partial sums are
+    // formed in the same order and the totals are the same bits whichever kernel produced them.  The search
+    // is over (the cluster barriers above were CTA barriers too): its point buffer is free.
+    double *s_r = sm.pts;
+    int *s_flag = s_qcol;
+    s_flag[threadIdx.x] = 0;
+    __syncthreads();
+    if (winner) {
+        const double *np = map.pts + (base + key) * 3;
+        const int t = qc - c0;
+        s_r[t * 3] = dsub(ori.x, np[0]);
+        s_r[t * 3 + 1] = dsub(ori.y, np[1]);
+        s_r[t * 3 + 2] = dsub(ori.z, np[2]);
+        s_flag[t] = 1;
+    }
+    __syncthreads();
+    const bool mine = s_flag[threadIdx.x] != 0;
+    const double rx = mine ? s_r[threadIdx.x * 3] : 0.0, ry = mine ? s_r[threadIdx.x * 3 + 1] : 0.0,
+                 rz = mine ? s_r[threadIdx.x * 3 + 2] : 0.0;
+    block_post_stats(ss, mine, rx, ry, rz, part, mail);
+}
+
+bool dedupe_stats_supported(int cols) { return div_up(cols, kTile) <= 8; }  // portable cluster size
+
+int launch_dedupe_stats(const double *cloud, const int *labels, const RowMap &map, const MatchOut &out,
+                        const PoseBatch &poses, int n_seq, int rows, int cols, cudaStream_t stream, double *part,
+                        const FitMailbox &mail) {
+    const int tiles = div_up(cols, kTile);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_seq * rows * tiles));
+    cfg.blockDim = dim3(kTile);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)tiles;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, k_dedupe_stats, cloud, labels, map, out, poses, rows, cols, tiles, part, mail);
+}
+
+int launch_loop_step(const double *cloud, const int *labels, const RowMap &map, const MatchOut &out,
+                     const PoseBatch &poses, int n_seq, int rows, int cols, cudaStream_t stream,
+                     const double *prev_cloud, const int *prev_labels, const PoseBatch &prev_poses, bool do_map,
+                     double *part, const FitMailbox &mail) {
+    const int tiles = div_up(cols, kTile);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_seq * rows * tiles));
+    cfg.blockDim = dim3(kTile);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)tiles;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, k_loop_step, cloud, labels, map, out, poses, rows, cols, tiles, prev_cloud,
+                                   prev_labels, prev_poses, do_map ? 1 : 0, part, mail);
 }
 
 size_t dedupe_smem_bytes(int cols) { return (size_t)cols * 16; }
@@ -603,9 +945,11 @@ int configure_row_kernels(int cols) {
 
 void launch_dedupe(const double *cloud, const int *labels, const RowMap &map, const MatchOut &out,
                    const PoseBatch &poses, int n_seq, int rows, int cols, cudaStream_t stream, double *row_stats,
-                   bool write_corr) {
+                   bool write_corr, const FitMailbox *mail) {
+    FitMailbox mb = {nullptr, nullptr, 0ull};
+    if (mail && row_stats && n_seq == 1) mb = *mail;
     k_dedupe_rows<<<n_seq * rows, kRowThreads, dedupe_smem_bytes(cols), stream>>>(
-        cloud, labels, map, out, poses, rows, cols, row_stats, write_corr ? 1 : 0);
+        cloud, labels, map, out, poses, rows, cols, row_stats, write_corr ? 1 : 0, mb);
 }
 
 // rows of one sequence back to back: corr_out[seq][offset(row) + i]

@@ -880,6 +880,16 @@ def test_closed_loop_with_prefetch_equals_blocking_loop(pkg, oracle, synth, shap
     for (pa, ea, na), (pb, eb, nb) in zip(a, b):
         assert np.array_equal(pa, pb) and ea == eb and na == nb
     assert np.array_equal(ga, gb)
+    # the same loop as ONE call (nav_slam_run, prediction = last + step): same poses, same final map
+    ctx = pkg.Context(r, c, device=0)
+    ctx.slam_init(np.zeros(6), clouds[0], want_global=False)
+    src = h_depth if use_depth else h
+    poses, errs, ncs = ctx.slam_run([src[f].data_ptr() for f in range(1, frames)], np.tile(step, (frames - 1, 1)),
+                                    np.zeros(6), depth_input=use_depth)
+    for f in range(frames - 1):
+        assert np.array_equal(poses[f], a[f][0]) and errs[f] == a[f][1] and ncs[f] == a[f][2]
+    assert np.array_equal(ctx.slam_mapping(poses[-1], None), ga)
+    ctx.close()
     slam = oracle.slam(r, c, 1)
     slam.init(np.zeros(6), clouds[0])
     last = np.zeros(6)
