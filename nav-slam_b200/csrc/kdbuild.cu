@@ -748,6 +748,7 @@ k_kd_level_cta(KdSoA cur, KdSoA nxt, int n, int level, int rule, const SegBox *_
 // them sorted for the levels below.
 constexpr int kFinThreads = 512;
 constexpr int kFinItems = kFinSeg / kFinThreads;
+constexpr int kFinBucket = 48;  // points per bin the counting sort still ranks by brute force
 struct FinSmem {
     u64 K[3][kFinSeg];
     int gid[kFinSeg];
@@ -755,7 +756,7 @@ struct FinSmem {
     unsigned sc[kFinSeg];           // exclusive prefix, lefts | medians << 16
     unsigned char ax[kFinSeg];      // split axis of the node at a position
     unsigned char side[kFinSeg];    // left / median / right code per local id
-    unsigned wsum[kFinThreads / 32];
+    unsigned wsum[1 + kFinThreads / 32];
 };
 
 __global__ void __launch_bounds__(kFinThreads)
@@ -786,22 +787,91 @@ k_kd_finish(KdSoA in, int n, int level0, int rule, KdNode *__restrict__ nodes, d
         sm.ax[i] = 0;
     }
     __syncthreads();
-    // three bitonic argsorts sharing their barriers
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < 3 * (P >> 1); t += kFinThreads) {
-                const int d = t / (P >> 1), u = t % (P >> 1);
-                const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1)), l = i + j;
-                unsigned short *perm = sm.lst[0][d];
-                const unsigned a = perm[i], b = perm[l];
-                const bool up = (i & k) == 0;
-                if (perm_greater(a, b, m, sm.K[d], sm.gid) == up) {
-                    perm[i] = (unsigned short)b;
-                    perm[l] = (unsigned short)a;
-                }
+    // Sort the three index lists, one per axis, by (key, index).  Counting sort: with as many bins as there
+    // are points (kFinSeg bins over the segment's key range on that axis) a bin holds one or two points on
+    // ordinary data, so one histogram, one scan and a brute-force ranking inside each bin order the list in
+    // O(m) -- the bitonic network (66 stages of 3 x 1024 compare-exchanges for 2048 points) was 60 % of this
+    // kernel.  An axis with a crowded bin (equal or nearly equal keys: walls in integer data) takes the
+    // bitonic network instead.
+    const SegBox sbox = box0[blockIdx.x];
+    for (int d = 0; d < 3; ++d) {
+        const u64 klo = sbox.lo[d];
+        const int shift = bin_shift(sbox.hi[d] - klo);
+        for (int i = tid; i < kFinSeg; i += kFinThreads) sm.sc[i] = 0u;
+        if (tid == 0) sm.wsum[0] = 0u;
+        __syncthreads();
+        unsigned bin[kFinItems], slot[kFinItems];
+#pragma unroll
+        for (int k = 0; k < kFinItems; ++k) {
+            const int i = tid + k * kFinThreads;
+            bin[k] = 0u;
+            slot[k] = 0u;
+            if (i < m) {
+                bin[k] = (unsigned)((sm.K[d][i] - klo) >> shift);
+                slot[k] = atomicAdd(&sm.sc[bin[k]], 1u);
             }
-            __syncthreads();
         }
+        __syncthreads();
+        // exclusive scan of the bin counts (in place); the largest bin decides fast path / fallback
+        {
+            unsigned cnt[kFinItems], run = 0, big = 0;
+#pragma unroll
+            for (int k = 0; k < kFinItems; ++k) {
+                cnt[k] = sm.sc[kFinItems * tid + k];
+                run += cnt[k];
+                big = max(big, cnt[k]);
+            }
+            unsigned inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(kFullMask, inc, o);
+                if (lane >= o) inc += t;
+            }
+            big = __reduce_max_sync(kFullMask, big);
+            __syncthreads();  // everybody has read its counts and wsum[0] is initialised
+            if (lane == 31) sm.wsum[1 + warp] = inc;
+            if (lane == 0 && big > (unsigned)kFinBucket) atomicMax(&sm.wsum[0], big);
+            __syncthreads();
+            unsigned base = 0;
+            for (int w = 0; w < warp; ++w) base += sm.wsum[1 + w];
+            unsigned ex = base + inc - run;
+#pragma unroll
+            for (int k = 0; k < kFinItems; ++k) {
+                sm.sc[kFinItems * tid + k] = ex;
+                ex += cnt[k];
+            }
+        }
+        __syncthreads();
+        unsigned short *perm = sm.lst[0][d], *tmp = sm.lst[1][d];
+        if (sm.wsum[0] > (unsigned)kFinBucket) {  // crowded bin: bitonic network on this axis (CTA-uniform branch)
+            __syncthreads();
+            for (int i = tid; i < kFinSeg; i += kFinThreads) perm[i] = i < m ? (unsigned short)i : (unsigned short)0xffffu;
+            __syncthreads();
+            bitonic_argsort<kFinThreads>(perm, P, m, sm.K[d], sm.gid);
+            continue;
+        }
+#pragma unroll
+        for (int k = 0; k < kFinItems; ++k) {
+            const int i = tid + k * kFinThreads;
+            if (i < m) tmp[sm.sc[bin[k]] + slot[k]] = (unsigned short)i;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kFinItems; ++k) {
+            const int i = tid + k * kFinThreads;
+            if (i >= m) continue;
+            const int bs = (int)sm.sc[bin[k]], be = bin[k] + 1 < (unsigned)kFinSeg ? (int)sm.sc[bin[k] + 1] : m;
+            const u64 key = sm.K[d][i];
+            const int id = sm.gid[i];
+            int rank = 0;
+            for (int j = bs; j < be; ++j) {
+                const int o = tmp[j];
+                const u64 ko = sm.K[d][o];
+                rank += (ko < key || (ko == key && sm.gid[o] < id)) ? 1 : 0;
+            }
+            perm[bs + rank] = (unsigned short)i;
+        }
+        __syncthreads();
     }
     // this thread owns positions kFinItems*tid .. +kFinItems-1 (relative to LO); lo_r/hi_r: their current
     // sub-segment, hi_r < 0 once the position has become a node
