@@ -147,8 +147,7 @@ struct BoxAcc {
         lo[2] = umin64(lo[2], c);
         hi[2] = umax64(hi[2], c);
     }
-    // warp reduction, then one shared-memory atomic per value from lane 0
-    __device__ __forceinline__ void commit(SegBox *s_box) {
+    __device__ __forceinline__ void warp_reduce() {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
 #pragma unroll
@@ -157,15 +156,41 @@ struct BoxAcc {
                 hi[d] = umax64(hi[d], __shfl_xor_sync(kFullMask, hi[d], o));
             }
         }
-        if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                if (lo[d] != ~0ull) atomicMin(&s_box->lo[d], lo[d]);
-                if (hi[d] != 0ull) atomicMax(&s_box->hi[d], hi[d]);
-            }
-        }
     }
 };
+
+// Merges the running boxes of all threads of the CTA into s_box[0] (from a) and s_box[1] (from b): warp
+// reduction, one row of twelve values per warp in shared memory, then twelve threads fold the rows.  (64-bit
+// min / max atomics on shared memory are compare-and-swap loops: sixteen warps contending for the same
+// twelve words cost microseconds.)  Called by all T threads; contains two barriers.
+template <int T>
+__device__ __forceinline__ void commit_boxes(BoxAcc &a, BoxAcc &b, SegBox *s_box, u64 (*s_part)[12]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a.warp_reduce();
+    b.warp_reduce();
+    if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            s_part[warp][d] = a.lo[d];
+            s_part[warp][3 + d] = a.hi[d];
+            s_part[warp][6 + d] = b.lo[d];
+            s_part[warp][9 + d] = b.hi[d];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const int v = threadIdx.x, d = v % 3;
+        const bool is_min = (v % 6) < 3;
+        SegBox &dst = s_box[v / 6];
+        u64 acc = is_min ? dst.lo[d] : dst.hi[d];
+        for (int w = 0; w < T / 32; ++w) acc = is_min ? umin64(acc, s_part[w][v]) : umax64(acc, s_part[w][v]);
+        if (is_min)
+            dst.lo[d] = acc;
+        else
+            dst.hi[d] = acc;
+    }
+    __syncthreads();
+}
 
 __device__ __forceinline__ void box_reset(SegBox *b) {
 #pragma unroll
@@ -179,11 +204,13 @@ __device__ __forceinline__ void box_reset(SegBox *b) {
 // keys + root bounding box
 __global__ void __launch_bounds__(256)
 k_kd_keys(const double *__restrict__ pts, int n, KdSoA out, SegBox *__restrict__ box0) {
-    __shared__ SegBox s_box;
-    if (threadIdx.x == 0) box_reset(&s_box);
+    __shared__ SegBox s_box[2];
+    __shared__ u64 s_part[256 / 32][12];
+    if (threadIdx.x < 2) box_reset(&s_box[threadIdx.x]);
     __syncthreads();
-    BoxAcc acc;
+    BoxAcc acc, none;
     acc.reset();
+    none.reset();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const u64 a = order_key(pts[(long long)i * 3]), b = order_key(pts[(long long)i * 3 + 1]),
                   c = order_key(pts[(long long)i * 3 + 2]);
@@ -193,11 +220,10 @@ k_kd_keys(const double *__restrict__ pts, int n, KdSoA out, SegBox *__restrict__
         out.id[i] = i;
         acc.add(a, b, c);
     }
-    acc.commit(&s_box);
-    __syncthreads();
+    commit_boxes<256>(acc, none, s_box, s_part);
     if (threadIdx.x < 3) {
-        atomicMin(&box0->lo[threadIdx.x], s_box.lo[threadIdx.x]);
-        atomicMax(&box0->hi[threadIdx.x], s_box.hi[threadIdx.x]);
+        atomicMin(&box0->lo[threadIdx.x], s_box[0].lo[threadIdx.x]);
+        atomicMax(&box0->hi[threadIdx.x], s_box[0].hi[threadIdx.x]);
     }
 }
 
@@ -263,6 +289,7 @@ struct KdSmem {
     unsigned hist[kBins];
     unsigned short perm[kCap];
     SegBox box[2];        // accumulated bounding boxes of the left / right half
+    u64 part[kCtaThreads / 32][12];  // per-warp rows of commit_boxes
     unsigned wsum[32];
     int res[4];
     unsigned cnt[4];
@@ -347,9 +374,7 @@ __device__ void resolve_region(KdSmem &sm, const KdSoA &out, const KdSoA &scratc
                 sm.piv_id = sm.ID[src];
             }
         }
-        accL.commit(&sm.box[0]);
-        accR.commit(&sm.box[1]);
-        __syncthreads();
+        commit_boxes<T>(accL, accR, sm.box, sm.part);
         return;
     }
     // ---- more candidates than fit: narrow the key range (then the index range) with further histogram
@@ -472,9 +497,7 @@ __device__ void resolve_region(KdSmem &sm, const KdSoA &out, const KdSoA &scratc
             sm.piv_id = id;
         }
     }
-    accL.commit(&sm.box[0]);
-    accR.commit(&sm.box[1]);
-    __syncthreads();
+    commit_boxes<T>(accL, accR, sm.box, sm.part);
 }
 
 __device__ __forceinline__ void emit_node(KdNode *nodes, int pos, const u64 key[3], int id, int axis) {
@@ -525,6 +548,7 @@ k_kd_partition(KdSoA cur, KdSoA nxt, int n, int level, int rule, int cps, const 
     __shared__ unsigned s_w[kPartThreads / 32][3];
     __shared__ unsigned s_base[3];
     __shared__ SegBox s_box[2];
+    __shared__ u64 s_part[kPartThreads / 32][12];
     const int s = blockIdx.x / cps, j = blockIdx.x % cps;
     int lo, hi;
     if (!segment_range(s, n, level, lo, hi)) return;
@@ -611,9 +635,7 @@ k_kd_partition(KdSoA cur, KdSoA nxt, int n, int level, int rule, int cps, const 
         run_c += __popc(bc);
         run_r += __popc(br);
     }
-    accL.commit(&s_box[0]);
-    accR.commit(&s_box[1]);
-    __syncthreads();
+    commit_boxes<kPartThreads>(accL, accR, s_box, s_part);
     if (tid < 6) {
         const int side = tid / 3, d = tid % 3;
         SegBox *dst = &box_next[2 * s + side];
@@ -729,9 +751,7 @@ k_kd_level_cta(KdSoA cur, KdSoA nxt, int n, int level, int rule, const SegBox *_
             nxt.id[pos] = id;
         }
     }
-    accL.commit(&sm.box[0]);
-    accR.commit(&sm.box[1]);
-    __syncthreads();  // also: the candidates written above are visible to the whole CTA
+    commit_boxes<kCtaThreads>(accL, accR, sm.box, sm.part);  // its barriers also publish the candidates written above
     u64 klo, khi;
     bin_range(sp, box_cur[s].hi[sp.axis], b, klo, khi);
     resolve_region<kCtaThreads>(sm, nxt, cur, lo + below, cnt, m - below, sp.axis, klo, khi);
