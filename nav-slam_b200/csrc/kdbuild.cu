@@ -288,6 +288,7 @@ struct KdSmem {
     int ID[kCap];
     unsigned hist[kBins];
     unsigned short perm[kCap];
+    unsigned short tmp[kCap];
     SegBox box[2];        // accumulated bounding boxes of the left / right half
     u64 part[kCtaThreads / 32][12];  // per-warp rows of commit_boxes
     unsigned wsum[32];
@@ -330,6 +331,90 @@ __device__ __forceinline__ int pow2_at_least(int c) {
     return P;
 }
 
+// Argsort of c <= kBins elements by (key, index) in O(c): counting sort over kBins bins of the key range
+// [klo, khi] -- with about as many bins as elements a bin holds one or two of them on ordinary data -- and a
+// brute-force ranking inside each bin.  perm[0..c) receives the order; tmp is a scratch list, hist kBins words,
+// wsum 1 + T/32 words.  Returns false, leaving perm undefined, when some bin holds more than kBucketMax elements
+// (equal or nearly equal keys): the caller then takes the bitonic network.  Called by all T threads; the
+// result is CTA-uniform; ends with a barrier.
+constexpr int kBucketMax = 48;
+template <int T>
+__device__ __forceinline__ bool counting_argsort(unsigned short *perm, unsigned short *tmp, unsigned *hist, unsigned *wsum,
+                                                 int c, const u64 *key, const int *id, u64 klo, u64 khi) {
+    constexpr int kPer = kBins / T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int shift = bin_shift(khi - klo);
+    for (int i = tid; i < kBins; i += T) hist[i] = 0u;
+    if (tid == 0) wsum[0] = 0u;
+    __syncthreads();
+    unsigned bin[kPer], slot[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int i = tid + k * T;
+        bin[k] = 0u;
+        slot[k] = 0u;
+        if (i < c) {
+            bin[k] = (unsigned)((key[i] - klo) >> shift);
+            slot[k] = atomicAdd(&hist[bin[k]], 1u);
+        }
+    }
+    __syncthreads();
+    {   // exclusive scan of the bin counts, in place; the fullest bin decides between fast path and fallback
+        unsigned cnt[kPer], run = 0, big = 0;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            cnt[k] = hist[kPer * tid + k];
+            run += cnt[k];
+            big = max(big, cnt[k]);
+        }
+        unsigned inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(kFullMask, inc, o);
+            if (lane >= o) inc += t;
+        }
+        big = __reduce_max_sync(kFullMask, big);
+        if (lane == 31) wsum[1 + warp] = inc;
+        if (lane == 0 && big > (unsigned)kBucketMax) atomicMax(&wsum[0], big);
+        __syncthreads();
+        const unsigned before = lane < warp ? wsum[1 + lane] : 0u;  // T / 32 <= 32 warps
+        unsigned ex = __reduce_add_sync(kFullMask, before) + inc - run;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            hist[kPer * tid + k] = ex;
+            ex += cnt[k];
+        }
+    }
+    __syncthreads();
+    if (wsum[0] > (unsigned)kBucketMax) {
+        __syncthreads();  // everybody has read the flag before it can be reset by a following call
+        return false;
+    }
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int i = tid + k * T;
+        if (i < c) tmp[hist[bin[k]] + slot[k]] = (unsigned short)i;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int i = tid + k * T;
+        if (i >= c) continue;
+        const int bs = (int)hist[bin[k]], be = bin[k] + 1 < (unsigned)kBins ? (int)hist[bin[k] + 1] : c;
+        const u64 mine = key[i];
+        const int my_id = id[i];
+        int rank = 0;
+        for (int j = bs; j < be; ++j) {
+            const int o = tmp[j];
+            const u64 ko = key[o];
+            rank += (ko < mine || (ko == mine && id[o] < my_id)) ? 1 : 0;
+        }
+        perm[bs + rank] = (unsigned short)i;
+    }
+    __syncthreads();
+    return true;
+}
+
 // Orders the candidate region out[a, a+c) so that the element of rank r (composite order on `axis`) sits at
 // a + r, everything smaller in front of it and everything larger behind it; accumulates the keys of the
 // elements in front / behind into sm.box[0] / sm.box[1]; leaves the pivot in sm.piv_*.  klo..khi bound the
@@ -342,20 +427,19 @@ __device__ void resolve_region(KdSmem &sm, const KdSoA &out, const KdSoA &scratc
     accL.reset();
     accR.reset();
     if (c <= kCap) {
-        const int P = pow2_at_least(c);
-        for (int t = tid; t < P; t += T) {
-            if (t < c) {
-                sm.K[0][t] = out.k[0][a + t];
-                sm.K[1][t] = out.k[1][a + t];
-                sm.K[2][t] = out.k[2][a + t];
-                sm.ID[t] = out.id[a + t];
-                sm.perm[t] = (unsigned short)t;
-            } else {
-                sm.perm[t] = 0xffffu;
-            }
+        for (int t = tid; t < c; t += T) {
+            sm.K[0][t] = out.k[0][a + t];
+            sm.K[1][t] = out.k[1][a + t];
+            sm.K[2][t] = out.k[2][a + t];
+            sm.ID[t] = out.id[a + t];
         }
         __syncthreads();
-        bitonic_argsort<T>(sm.perm, P, c, sm.K[axis], sm.ID);
+        if (!counting_argsort<T>(sm.perm, sm.tmp, sm.hist, sm.wsum, c, sm.K[axis], sm.ID, klo, khi)) {
+            const int P = pow2_at_least(c);
+            for (int t = tid; t < P; t += T) sm.perm[t] = t < c ? (unsigned short)t : (unsigned short)0xffffu;
+            __syncthreads();
+            bitonic_argsort<T>(sm.perm, P, c, sm.K[axis], sm.ID);
+        }
         for (int t = tid; t < c; t += T) {
             const int src = sm.perm[t];
             const u64 k0 = sm.K[0][src], k1 = sm.K[1][src], k2 = sm.K[2][src];
@@ -530,8 +614,20 @@ k_kd_hist(KdSoA cur, int n, int level, int rule, int cps, const SegBox *__restri
     for (int t = threadIdx.x; t < kBins; t += kPartThreads) s_hist[t] = 0u;
     __syncthreads();
     const u64 *ka = cur.k[sp.axis];
-    for (int e = start + threadIdx.x; e < end; e += kPartThreads)
-        atomicAdd(&s_hist[(unsigned)((ka[e] - sp.base) >> sp.shift)], 1u);
+    {   // all of the thread's keys are loaded before the first shared-memory atomic (the loop with the atomic
+        // inside was bound by one load latency per iteration)
+        u64 kv[kPartItems];
+#pragma unroll
+        for (int it = 0; it < kPartItems; ++it) {
+            const int e = start + it * kPartThreads + threadIdx.x;
+            kv[it] = e < end ? ka[e] : 0ull;
+        }
+#pragma unroll
+        for (int it = 0; it < kPartItems; ++it) {
+            const int e = start + it * kPartThreads + threadIdx.x;
+            if (e < end) atomicAdd(&s_hist[(unsigned)((kv[it] - sp.base) >> sp.shift)], 1u);
+        }
+    }
     __syncthreads();
     unsigned *g = ghist + (size_t)s * kBins;
     for (int t = threadIdx.x; t < kBins; t += kPartThreads)
@@ -700,7 +796,17 @@ k_kd_level_cta(KdSoA cur, KdSoA nxt, int n, int level, int rule, const SegBox *_
     if (tid < 4) sm.cnt[tid] = 0u;
     __syncthreads();
     const u64 *ka = cur.k[sp.axis];
-    for (int e = lo + tid; e < hi; e += kCtaThreads) atomicAdd(&sm.hist[(unsigned)((ka[e] - sp.base) >> sp.shift)], 1u);
+    for (int e0 = lo; e0 < hi; e0 += 8 * kCtaThreads) {  // eight loads in flight per thread in front of the atomics
+        u64 kv[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int e = e0 + it * kCtaThreads + tid;
+            kv[it] = e < hi ? ka[e] : 0ull;
+        }
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+            if (e0 + it * kCtaThreads + tid < hi) atomicAdd(&sm.hist[(unsigned)((kv[it] - sp.base) >> sp.shift)], 1u);
+    }
     __syncthreads();
     const int m = (hi - lo) >> 1;
     int b, below, cnt;
@@ -767,8 +873,8 @@ k_kd_level_cta(KdSoA cur, KdSoA nxt, int n, int level, int rule, const SegBox *_
 // partitioned inside every sub-segment (prefix sum of packed left / median counts + scatter), which keeps
 // them sorted for the levels below.
 constexpr int kFinThreads = 512;
+static_assert(kFinSeg == kBins, "the finisher's counting sort uses one bin per slot of the segment");
 constexpr int kFinItems = kFinSeg / kFinThreads;
-constexpr int kFinBucket = 48;  // points per bin the counting sort still ranks by brute force
 struct FinSmem {
     u64 K[3][kFinSeg];
     int gid[kFinSeg];
@@ -815,83 +921,12 @@ k_kd_finish(KdSoA in, int n, int level0, int rule, KdNode *__restrict__ nodes, d
     // bitonic network instead.
     const SegBox sbox = box0[blockIdx.x];
     for (int d = 0; d < 3; ++d) {
-        const u64 klo = sbox.lo[d];
-        const int shift = bin_shift(sbox.hi[d] - klo);
-        for (int i = tid; i < kFinSeg; i += kFinThreads) sm.sc[i] = 0u;
-        if (tid == 0) sm.wsum[0] = 0u;
-        __syncthreads();
-        unsigned bin[kFinItems], slot[kFinItems];
-#pragma unroll
-        for (int k = 0; k < kFinItems; ++k) {
-            const int i = tid + k * kFinThreads;
-            bin[k] = 0u;
-            slot[k] = 0u;
-            if (i < m) {
-                bin[k] = (unsigned)((sm.K[d][i] - klo) >> shift);
-                slot[k] = atomicAdd(&sm.sc[bin[k]], 1u);
-            }
-        }
-        __syncthreads();
-        // exclusive scan of the bin counts (in place); the largest bin decides fast path / fallback
-        {
-            unsigned cnt[kFinItems], run = 0, big = 0;
-#pragma unroll
-            for (int k = 0; k < kFinItems; ++k) {
-                cnt[k] = sm.sc[kFinItems * tid + k];
-                run += cnt[k];
-                big = max(big, cnt[k]);
-            }
-            unsigned inc = run;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(kFullMask, inc, o);
-                if (lane >= o) inc += t;
-            }
-            big = __reduce_max_sync(kFullMask, big);
-            __syncthreads();  // everybody has read its counts and wsum[0] is initialised
-            if (lane == 31) sm.wsum[1 + warp] = inc;
-            if (lane == 0 && big > (unsigned)kFinBucket) atomicMax(&sm.wsum[0], big);
-            __syncthreads();
-            unsigned base = 0;
-            for (int w = 0; w < warp; ++w) base += sm.wsum[1 + w];
-            unsigned ex = base + inc - run;
-#pragma unroll
-            for (int k = 0; k < kFinItems; ++k) {
-                sm.sc[kFinItems * tid + k] = ex;
-                ex += cnt[k];
-            }
-        }
-        __syncthreads();
-        unsigned short *perm = sm.lst[0][d], *tmp = sm.lst[1][d];
-        if (sm.wsum[0] > (unsigned)kFinBucket) {  // crowded bin: bitonic network on this axis (CTA-uniform branch)
-            __syncthreads();
+        unsigned short *perm = sm.lst[0][d];
+        if (!counting_argsort<kFinThreads>(perm, sm.lst[1][d], sm.sc, sm.wsum, m, sm.K[d], sm.gid, sbox.lo[d], sbox.hi[d])) {
             for (int i = tid; i < kFinSeg; i += kFinThreads) perm[i] = i < m ? (unsigned short)i : (unsigned short)0xffffu;
             __syncthreads();
             bitonic_argsort<kFinThreads>(perm, P, m, sm.K[d], sm.gid);
-            continue;
         }
-#pragma unroll
-        for (int k = 0; k < kFinItems; ++k) {
-            const int i = tid + k * kFinThreads;
-            if (i < m) tmp[sm.sc[bin[k]] + slot[k]] = (unsigned short)i;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < kFinItems; ++k) {
-            const int i = tid + k * kFinThreads;
-            if (i >= m) continue;
-            const int bs = (int)sm.sc[bin[k]], be = bin[k] + 1 < (unsigned)kFinSeg ? (int)sm.sc[bin[k] + 1] : m;
-            const u64 key = sm.K[d][i];
-            const int id = sm.gid[i];
-            int rank = 0;
-            for (int j = bs; j < be; ++j) {
-                const int o = tmp[j];
-                const u64 ko = sm.K[d][o];
-                rank += (ko < key || (ko == key && sm.gid[o] < id)) ? 1 : 0;
-            }
-            perm[bs + rank] = (unsigned short)i;
-        }
-        __syncthreads();
     }
     // this thread owns positions kFinItems*tid .. +kFinItems-1 (relative to LO); lo_r/hi_r: their current
     // sub-segment, hi_r < 0 once the position has become a node
@@ -955,9 +990,8 @@ k_kd_finish(KdSoA in, int n, int level0, int rule, KdNode *__restrict__ nodes, d
             }
             if (lane == 31) sm.wsum[warp] = inc;
             __syncthreads();
-            unsigned base = 0;
-            for (int w = 0; w < warp; ++w) base += sm.wsum[w];
-            unsigned ex = base + inc - run;
+            const unsigned before = lane < warp ? sm.wsum[lane] : 0u;
+            unsigned ex = __reduce_add_sync(kFullMask, before) + inc - run;
 #pragma unroll
             for (int k = 0; k < kFinItems; ++k) {
                 sm.sc[kFinItems * tid + k] = ex;
