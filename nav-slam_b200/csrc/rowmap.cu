@@ -277,7 +277,7 @@ __device__ __forceinline__ void prefetch_neighbourhood(MapSmem &sm, const RowVie
 // box hierarchy.  best = smallest dsq (INFINITY if the row map is empty), bcol = its column (lowest on ties).
 template <bool kCoherent>
 __device__ __forceinline__ void search_row(const MapSmem &sm, const RowView &rv, int qc, const P3 &q, double &best,
-                                           int &bcol) {
+                                           int &bcol, unsigned wmask) {
     const double *m_pts = rv.pts;
     const unsigned *m_mask = rv.mask;
     const float4 *m_box = rv.box, *m_sbox = rv.sbox;
@@ -316,7 +316,66 @@ __device__ __forceinline__ void search_row(const MapSmem &sm, const RowView &rv,
             best_up = __double2float_ru(best);
         }
     }
-    // everything else through the box hierarchy (exactness does not depend on the order of visits)
+    // Everything else through the boxes (exactness does not depend on the order of visits).
+    // Rows whose leaf boxes are all in shared memory (<= 2048 columns): WARP-COOPERATIVE culling.  The 32 lanes
+    // hold queries of neighbouring columns, so their candidate sets are nearly the same; instead of every lane
+    // testing 8 super boxes and 16-48 leaf boxes, the warp tests every leaf box of the row ONCE -- lane l takes
+    // leaves l, l+32, ... -- against the bounding box of the warp's 32 queries and the loosest of their bounds.
+    // That test is a lower bound of every lane's own test (gaps to a bigger box are smaller, rounding down is
+    // monotone), so the surviving leaves are a superset of what any lane needs.  Each lane then tests only the
+    // survivors against its own query (a warp-uniform loop over a handful of leaves) and scans the ones that pass.
+    if (row_in_smem && wmask == kFull) {
+        const unsigned lane = threadIdx.x & 31u;
+        float wdn[3], wup[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            wdn[d] = float_from_order_key(__reduce_min_sync(kFull, float_order_key(q32.dn[d])));
+            wup[d] = float_from_order_key(__reduce_max_sync(kFull, float_order_key(q32.up[d])));
+        }
+        // best_up >= 0 (or +inf): such floats order like their bit patterns
+        const float wbest = __int_as_float(__reduce_max_sync(kFull, __float_as_int(best_up)));
+        Q32 wq;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            wq.dn[d] = wdn[d];
+            wq.up[d] = wup[d];
+        }
+        constexpr int kWords = kMaxRowLeafSmem / 32;
+        unsigned surv[kWords];
+#pragma unroll
+        for (int k = 0; k < kWords; ++k) {
+            const int lf = k * 32 + (int)lane;
+            bool keep = false;
+            if (lf < n_leaf) keep = !(box_lower_bound32(sm.rbox[lf * 2], sm.rbox[lf * 2 + 1], wq) > wbest);
+            surv[k] = __ballot_sync(kFull, keep);
+        }
+        // the leaves visited above are done
+#pragma unroll
+        for (int k = 0; k < kWords; ++k) {
+            unsigned own = 0;
+            for (unsigned w = surv[k]; w; w &= w - 1) {  // warp-uniform loop
+                const int b = __ffs(w) - 1, lf = k * 32 + b;
+                const bool pass = !(box_lower_bound32(sm.rbox[lf * 2], sm.rbox[lf * 2 + 1], q32) > best_up);
+                own |= (unsigned)pass << b;
+            }
+#pragma unroll
+            for (int d = -kNear; d <= kNear; ++d) {
+                const int j = seed + d - k * 32;
+                if (j >= 0 && j < 32) own &= ~(1u << j);
+            }
+            while (own) {
+                const int lf = k * 32 + __ffs(own) - 1, j = lf - leaf0;
+                own &= own - 1;
+                if (box_lower_bound32(sm.rbox[lf * 2], sm.rbox[lf * 2 + 1], q32) > best_up) continue;
+                if (j >= 0 && j < kNbLeaves)
+                    scan_leaf(sm.pts + j * kChunk * 3, sm.mask[j], lf * kChunk, q, best, bcol);
+                else
+                    scan_leaf(m_pts + (long long)lf * kChunk * 3, ld_map<kCoherent>(m_mask + lf), lf * kChunk, q, best, bcol);
+                best_up = __double2float_ru(best);
+            }
+        }
+        return;
+    }
     for (int sc = 0; sc < n_sup; ++sc) {
         const float4 slo = sup_in_smem ? sm.sbox[sc * 2] : ld_map<kCoherent>(m_sbox + sc * 2);
         const float4 shi = sup_in_smem ? sm.sbox[sc * 2 + 1] : ld_map<kCoherent>(m_sbox + sc * 2 + 1);
@@ -450,8 +509,11 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
     const int slot = block_excl_count(label == 1, s_warp, nq);  // its barriers also publish the prefetch
     if (label == 1) s_qcol[slot] = threadIdx.x;
     __syncthreads();
-    if ((int)threadIdx.x >= nq) return;
-    const int t = s_qcol[threadIdx.x];  // column-in-tile handled by this thread
+    // whole warps without a query leave; in the last warp with queries the spare lanes repeat its last query,
+    // so that the warp-cooperative part of the search always runs with 32 lanes (they store nothing)
+    if ((int)(threadIdx.x & ~31u) >= nq) return;
+    const bool has_query = (int)threadIdx.x < nq;
+    const int t = s_qcol[min((int)threadIdx.x, nq - 1)];  // column-in-tile handled by this thread
     const int qc = c0 + t;
     P3 p;
     if (kFusedLabels) {
@@ -466,7 +528,8 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
     const P3 q = shift_point(pose, xf_point(pose, p));
     double best;
     int bcol;
-    search_row<false>(sm, rv, qc, q, best, bcol);
+    search_row<false>(sm, rv, qc, q, best, bcol, kFull);
+    if (!has_query) return;
     out.nn_idx[base + qc] = bcol >= 0 ? row * cols + bcol : -1;
     out.nn_dist[base + qc] = bcol >= 0 ? __dsqrt_rn(best) : INFINITY;
 }
@@ -851,20 +914,25 @@ k_loop_step(const double *__restrict__ cloud, const int *__restrict__ labels, Ro
     int key = -1, qc = -1;
     unsigned long long dbits = 0;
     P3 ori = {0, 0, 0};
-    if ((int)threadIdx.x < nq) {
-        qc = c0 + s_qcol[threadIdx.x];
+    if ((int)(threadIdx.x & ~31u) < nq) {  // warps with at least one query; spare lanes repeat the last one
+        const bool has_query = (int)threadIdx.x < nq;
+        const int my_qc = c0 + s_qcol[min((int)threadIdx.x, nq - 1)];
         const PoseXf &pose = poses.p[seq];
-        ori = xf_point(pose, load_p3(cloud + (base + qc) * 3));
-        const P3 q = shift_point(pose, ori);
+        const P3 my_ori = xf_point(pose, load_p3(cloud + (base + my_qc) * 3));
+        const P3 q = shift_point(pose, my_ori);
         double best;
         int bcol;
-        search_row<true>(sm, rv, qc, q, best, bcol);
-        const double dist = bcol >= 0 ? __dsqrt_rn(best) : INFINITY;
-        out.nn_idx[base + qc] = bcol >= 0 ? row * cols + bcol : -1;
-        out.nn_dist[base + qc] = dist;
-        if (bcol >= 0) {
-            key = bcol;
-            dbits = (unsigned long long)__double_as_longlong(dist);
+        search_row<true>(sm, rv, my_qc, q, best, bcol, kFull);
+        if (has_query) {
+            qc = my_qc;
+            ori = my_ori;
+            const double dist = bcol >= 0 ? __dsqrt_rn(best) : INFINITY;
+            out.nn_idx[base + qc] = bcol >= 0 ? row * cols + bcol : -1;
+            out.nn_dist[base + qc] = dist;
+            if (bcol >= 0) {
+                key = bcol;
+                dbits = (unsigned long long)__double_as_longlong(dist);
+            }
         }
     }
     const bool winner = cluster_dedupe_winner(s_best, s_win, key, dbits, qc);
