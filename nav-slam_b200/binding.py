@@ -59,7 +59,8 @@ EXPORTS = [
 
 
 def lib_path() -> str:
-    return _build.LIB
+    # NAVSLAM_LIB: developer override (kernel variants built side by side for A/B timing, profiles/prof_frame.py)
+    return os.environ.get("NAVSLAM_LIB") or _build.LIB
 
 
 def load_library(build_if_missing: bool = True):

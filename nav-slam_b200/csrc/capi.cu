@@ -254,6 +254,16 @@ struct nav_ctx {
     double *h_fit = nullptr;
     unsigned *d_fit_ticket = nullptr;
     unsigned long long fit_seq = 0;
+    // poses of a sequence launch (nav_frontend_sequence_dev): device array + a ring of pinned staging buffers
+    static constexpr int kPoseRing = 4;
+    struct PoseRing {
+        void *host = nullptr;
+        size_t cap = 0;
+        cudaEvent_t done = nullptr;
+    } pose_ring[kPoseRing];
+    int pose_ring_next = 0;
+    void *d_pose = nullptr;
+    size_t d_pose_cap = 0;
     // NAV_RUN_TRACE=1: nav_slam_run prints where the host side of the closed loop spends its time
     // [prefetch call, launches of match + dedupe, wait for the statistics, fit, mapping call]
     bool trace = false;
@@ -353,6 +363,11 @@ extern "C" void nav_destroy(nav_ctx *c) {
     if (c->d_row_stats) cudaFree(c->d_row_stats);
     if (c->d_tile_stats) cudaFree(c->d_tile_stats);
     if (c->h_fit) cudaFreeHost(c->h_fit);
+    for (auto &pr : c->pose_ring) {
+        if (pr.host) cudaFreeHost(pr.host);
+        if (pr.done) cudaEventDestroy(pr.done);
+    }
+    if (c->d_pose) cudaFree(c->d_pose);
     if (c->d_fit_ticket) cudaFree(c->d_fit_ticket);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -1477,6 +1492,51 @@ extern "C" int nav_frontend_sequence_dev(nav_ctx *c, const void *dev_frames, siz
     if (!c->have_map) return fail("nav_frontend_sequence_dev: call nav_slam_init_dev first");
     const double *base = (const double *)dev_frames;
     order_after_async(c);
+    // One launch for the whole sequence (k_frame_seq: a thread-block cluster per image row walks through the
+    // frames with a cluster barrier per frame) when a row's tiles fit a cluster; NAV_SEQ_LAUNCHES=1 keeps one
+    // launch per frame.  The per-kernel profiler wants separate launches too.
+    // Measured (profiles/README.md): the same 14.4-14.5 us per 64x2048 frame as separate launches for one
+    // sequence -- the chain of one row is what takes that long -- with one launch instead of n_frames for the
+    // host to issue; several sequences side by side (n_seq > 1) fill the machine better as separate launches.
+    static const bool per_frame = getenv("NAV_SEQ_LAUNCHES") != nullptr;
+    if (!per_frame && !c->prof && c->n_seq == 1 && n_frames > 1 && frame_seq_supported(c->cols) && n_frames <= 0x7fffffff) {
+        const size_t n_pose = n_frames * (size_t)c->n_seq, bytes = n_pose * 2 * sizeof(PoseXf);
+        nav_ctx::PoseRing &pr = c->pose_ring[c->pose_ring_next];
+        c->pose_ring_next = (c->pose_ring_next + 1) % nav_ctx::kPoseRing;
+        if (pr.done) CU(cudaEventSynchronize(pr.done));  // the staging buffer's previous upload (several sequences ago)
+        if (pr.cap < bytes) {
+            if (pr.host) cudaFreeHost(pr.host);
+            pr.host = nullptr;
+            pr.cap = 0;
+            CU(cudaHostAlloc((void **)&pr.host, bytes, cudaHostAllocDefault));
+            pr.cap = bytes;
+        }
+        if (!pr.done) CU(cudaEventCreateWithFlags(&pr.done, cudaEventDisableTiming));
+        if (c->d_pose_cap < bytes) {
+            CU(cudaStreamSynchronize(c->stream));
+            if (c->d_pose) cudaFree(c->d_pose);
+            c->d_pose = nullptr;
+            c->d_pose_cap = 0;
+            CU(cudaMalloc((void **)&c->d_pose, bytes));
+            c->d_pose_cap = bytes;
+        }
+        PoseXf *loc = (PoseXf *)pr.host, *fin = loc + n_pose;
+        for (size_t i = 0; i < n_pose; ++i) {
+            loc[i] = make_pose(&pos_predict[i], &pos_last[i]);
+            fin[i] = make_pose(&pos_final[i], nullptr);
+        }
+        CU(cudaMemcpyAsync(c->d_pose, pr.host, bytes, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaEventRecord(pr.done, c->stream));
+        const MatchOut out = {c->d_nn_idx, c->d_nn_dist, c->d_corr_rows, c->d_corr_row_count};
+        CU((cudaError_t)launch_frame_seq(base, (long long)c->ntot * 3, (int)n_frames, c->d_labels, c->map, c->map_alt, out,
+                                         (const PoseXf *)c->d_pose, (const PoseXf *)c->d_pose + n_pose, c->n_seq, c->rows,
+                                         c->cols, c->d_n_exact, c->stream));
+        c->launches++;
+        if (n_frames & 1) std::swap(c->map, c->map_alt);
+        c->cloud_resident = false;
+        CU(cudaGetLastError());
+        return 0;
+    }
     for (size_t f = 0; f < n_frames; ++f) {
         const double *cl = base + f * c->ntot * 3;
         const size_t o = f * (size_t)c->n_seq;

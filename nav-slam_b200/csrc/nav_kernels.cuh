@@ -39,6 +39,14 @@ struct FitMailbox {
     unsigned long long seq;
 };
 
+// a whole sequence of frames with known poses in one launch (one thread-block cluster per image row walks
+// through the frames); map0 is searched by frame 0, frame f builds the map for frame f+1 in the other buffer.
+// d_pose_loc / d_pose_fin: device arrays [n_frames][n_seq].  Needs frame_seq_supported(cols).
+bool frame_seq_supported(int cols);
+int launch_frame_seq(const double *frames, long long frame_stride, int n_frames, int *labels, const RowMap &map0,
+                     const RowMap &map1, const MatchOut &out, const PoseXf *d_pose_loc, const PoseXf *d_pose_fin,
+                     int n_seq, int rows, int cols, unsigned *n_exact, cudaStream_t stream);
+
 size_t dedupe_smem_bytes(int cols);
 int configure_row_kernels(int cols);  // opt in to large dynamic shared memory; 0 on success
 

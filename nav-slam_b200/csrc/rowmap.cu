@@ -298,7 +298,10 @@ __device__ __forceinline__ void search_row(const MapSmem &sm, const RowView &rv,
     // Measured (64x2048, frames/s single sequence / 8 sequences per launch): kNear 2: 55.3 K / 55.9 K,
     // kNear 1: 57.8 K / 61.3 K, kNear 0: 49.5 K / 61.0 K -- one neighbour each side gives the mask tests below
     // a tight bound; a second one is rarely needed and costs two more box tests per query.
-    constexpr int kNear = 1;
+#ifndef NAV_MATCH_KNEAR
+#define NAV_MATCH_KNEAR 1
+#endif
+    constexpr int kNear = NAV_MATCH_KNEAR;
 #pragma unroll
     for (int d = 1; d <= kNear; ++d) {
 #pragma unroll
@@ -444,9 +447,9 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
               unsigned *__restrict__ n_exact, RowMap map_next, const __grid_constant__ PoseBatch final_poses,
               int pdl) {
     __shared__ StencilSmem s;
-    const int rid = blockIdx.x / tiles_per_row;
-    const int tile = blockIdx.x % tiles_per_row;
-    const int seq = rid / rows, row = rid % rows;
+    // grid = (tiles per row, rows, sequences): no integer divisions to find the tile
+    const int tile = blockIdx.x, row = blockIdx.y, seq = blockIdx.z;
+    const int rid = seq * rows + row;
     const long long base = (long long)rid * cols;
     const int c0 = tile * kTile;
     const int c = c0 + threadIdx.x;
@@ -534,6 +537,116 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
     out.nn_dist[base + qc] = bcol >= 0 ? __dsqrt_rn(best) : INFINITY;
 }
 
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// A whole SEQUENCE of frames with known poses in ONE launch (nav_frontend_sequence_dev).  Frame t+1 of an image
+// row only depends on the map the eight tiles of the SAME row built from frame t, so the CTAs of a row form a
+// thread-block cluster that walks through the frames on its own, with a cluster barrier per frame where
+// separate launches had a grid-wide dependency: no launch latency between frames, and rows that are ahead are
+// not held back by rows that are behind.  Per frame the body is that of k_frame_match<fused labels, fused map>:
+// labels (a3), query transform (a7), exact search of the row map of the previous frame (a6), the next map from
+// the frame's final pose into the other map buffer (a7, a4/a5).  labels / nn_idx / nn_dist hold the results of
+// the last frame, as after the same number of separate launches.
+struct SeqArgs {
+    const double *frames;     // [n_frames][n_seq*rows][cols][3]
+    long long frame_stride;   // doubles between consecutive frames
+    int n_frames, n_seq;
+    const PoseXf *pose_loc;   // [n_frames][n_seq] predicted pose + shift (queries)
+    const PoseXf *pose_fin;   // [n_frames][n_seq] final pose (map)
+};
+
+__global__ void __launch_bounds__(kTile, NAV_MATCH_MIN_CTAS)
+k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, MatchOut out, int rows, int cols,
+            unsigned *__restrict__ n_exact) {
+    __shared__ StencilSmem s;
+    __shared__ int s_warp[65];
+    __shared__ int s_qcol[kTile];
+    __shared__ MapSmem sm;
+    __shared__ float4 s_lo[kChunksPerSuper], s_hi[kChunksPerSuper];
+    const int tile = blockIdx.x, row = blockIdx.y, seq = blockIdx.z;
+    const int rid = seq * rows + row;
+    const long long base = (long long)rid * cols;
+    const int c0 = tile * kTile;
+    const int c = c0 + threadIdx.x;
+    for (int f = 0; f < a.n_frames; ++f) {
+        const double *cloud = a.frames + (long long)f * a.frame_stride;
+        const RowMap &map = (f & 1) ? map1 : map0;
+        const RowMap &map_next = (f & 1) ? map0 : map1;
+        const RowView rv = {map.pts + base * 3, map.mask + (long long)rid * map.n_chunks,
+                            map.box + (long long)rid * map.n_chunks * 2, map.sbox + (long long)rid * map.n_super * 2,
+                            map.n_chunks, map.n_super, tile * kChunksPerSuper - 1};
+        prefetch_neighbourhood<true>(sm, rv, cols);
+        tile_stage(s, cloud + base * 3, c0, cols);
+        __syncthreads();
+        const int label = tile_labels_filtered(s, c0, cols, n_exact);
+        if (c < cols) {
+            labels[base + c] = label;
+            if (label != 1) {
+                out.nn_idx[base + c] = -1;
+                out.nn_dist[base + c] = -1.0;
+            }
+        }
+        {
+            P3 own = {0, 0, 0};
+            if (c < cols) {
+                const double *sp = s.pts + (threadIdx.x + kHalo) * 3;
+                own.x = sp[0];
+                own.y = sp[1];
+                own.z = sp[2];
+            }
+            map_tile(label == 1, c < cols, own, a.pose_fin[(long long)f * a.n_seq + seq], map_next, rid, tile, c, base,
+                     s_lo, s_hi);
+        }
+        cp_async_wait_all();
+        int nq;
+        const int slot = block_excl_count(label == 1, s_warp, nq);  // its barriers also publish the prefetch
+        if (label == 1) s_qcol[slot] = threadIdx.x;
+        __syncthreads();
+        if ((int)(threadIdx.x & ~31u) < nq) {  // warps with at least one query; spare lanes repeat the last one
+            const int t = s_qcol[min((int)threadIdx.x, nq - 1)];
+            const int qc = c0 + t;
+            const double *sp = s.pts + (t + kHalo) * 3;
+            const P3 p = {sp[0], sp[1], sp[2]};
+            const PoseXf &pose = a.pose_loc[(long long)f * a.n_seq + seq];
+            const P3 q = shift_point(pose, xf_point(pose, p));
+            double best;
+            int bcol;
+            search_row<true>(sm, rv, qc, q, best, bcol, kFull);
+            if ((int)threadIdx.x < nq) {
+                out.nn_idx[base + qc] = bcol >= 0 ? row * cols + bcol : -1;
+                out.nn_dist[base + qc] = bcol >= 0 ? __dsqrt_rn(best) : INFINITY;
+            }
+        }
+        // the row's next map is complete and nobody of the row still reads the current one (also a CTA barrier:
+        // the shared-memory tiles are free for the next frame)
+        cluster_sync_all();
+    }
+}
+
+bool frame_seq_supported(int cols) { return div_up(cols, kTile) <= 8; }
+
+int launch_frame_seq(const double *frames, long long frame_stride, int n_frames, int *labels, const RowMap &map0,
+                     const RowMap &map1, const MatchOut &out, const PoseXf *d_pose_loc, const PoseXf *d_pose_fin,
+                     int n_seq, int rows, int cols, unsigned *n_exact, cudaStream_t stream) {
+    const int tiles = div_up(cols, kTile);
+    const SeqArgs a = {frames, frame_stride, n_frames, n_seq, d_pose_loc, d_pose_fin};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tiles, (unsigned)rows, (unsigned)n_seq);
+    cfg.blockDim = dim3(kTile);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = (unsigned)tiles;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, k_frame_seq, a, labels, map0, map1, out, rows, cols, n_exact);
+}
+
 void launch_frame_map(const double *cloud, const int *labels, const RowMap &map, const PoseBatch &poses,
                       int n_seq, int rows, int cols, cudaStream_t stream) {
     const int tiles = div_up(cols, kTile);
@@ -545,7 +658,7 @@ static void launch_match_variant(int grid, cudaStream_t stream, bool pdl, const 
                                  const RowMap &map, const MatchOut &out, const PoseBatch &poses, int rows, int cols,
                                  int tiles, unsigned *n_exact, const RowMap &map_next, const PoseBatch &final_poses) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
+    cfg.gridDim = dim3((unsigned)tiles, (unsigned)rows, (unsigned)(grid / (tiles * rows)));
     cfg.blockDim = dim3(kTile);
     cfg.stream = stream;
     cudaLaunchAttribute attr;
@@ -752,10 +865,6 @@ k_dedupe_rows(const double *__restrict__ cloud, const int *__restrict__ labels, 
 // column per thread: 23 us -> a few us per 64x2048 frame.
 // Partial sums: per CTA in a fixed order (shuffle tree, then warp by warp); the CTA that finishes last adds
 // the partials of the whole frame in a fixed order and posts the totals to the host mailbox.
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
-}
-
 // Phases 1-3 of the cluster dedupe.  Called by ALL threads of every CTA of the row's cluster (four cluster
 // barriers inside).  key = matched map column of this thread's query (or -1), dbits = bits of its distance,
 // c = the query's column.  Returns whether this query is the one kept for its map point.
