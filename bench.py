@@ -58,6 +58,18 @@ def load_pkg():
     return importlib.import_module("nav-slam_b200")
 
 
+_REAL_STDOUT = None
+
+
+def print_line(line):
+    txt = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(txt)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, txt.encode())
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -294,7 +306,7 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print_line(line)
 
 
 # ------------------------------------------------------------------ shim leg (child process) ----
@@ -884,7 +896,7 @@ def run_gpu_arm(args):
                         "the same stencil fed a batch reaches kernels.labels_batch.frac_of_hbm_peak"},
             "kernels": kernels, "batched_sequences": batched, "nn": nn, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        print_line(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -1032,6 +1044,12 @@ def main():
     if args.shim_leg:
         run_shim_leg(args)
         return
+    # stdout carries the ONE JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints
+    # its version there) are sent to stderr, and print_line() writes the line to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
