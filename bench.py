@@ -738,6 +738,8 @@ def run_gpu_arm(args):
         "map": NPX * (24 + 4 + 24) + side,
     }
     peak, tc_peak, peak_src = measured_peaks()
+    seq_mode = launches_per_rep < K          # the library ran the timed steps as one sequence launch
+    dom_kernel = "k_frame_seq" if seq_mode else "k_frame_match"
     kernels = {}
     for name, (ms, n) in prof.items():
         if n:
@@ -749,8 +751,14 @@ def run_gpu_arm(args):
                 # step time; the event-bracketed single launch is kept beside it
                 extra = {"us_per_launch_isolated": us}
                 us, n = 1e3 * dev_ms / K, K * n_reps
-            ach = alg_bytes[name] / (us * 1e-6) / 1e9
-            kernels[name] = {"us_per_launch": us, "launches": n, "alg_bytes_per_launch": alg_bytes[name],
+                if seq_mode:
+                    # the K timed steps are ONE launch of k_frame_seq (a thread-block cluster per image row walks
+                    # through the frames): K frames of algorithmic bytes per launch over that launch's duration
+                    extra.update({"frames_per_launch": K, "us_per_frame": us})
+                    us, n = 1e3 * dev_ms, n_reps
+            ab = alg_bytes[name] * (K if (seq_mode and name == "frame_fused") else 1)
+            ach = ab / (us * 1e-6) / 1e9
+            kernels[name] = {"us_per_launch": us, "launches": n, "alg_bytes_per_launch": ab,
                              "achieved_gbs": ach, "frac_of_hbm_peak": ach / peak, **extra}
     dom = "frame_fused" if "frame_fused" in kernels else (max(kernels, key=lambda k: kernels[k]["us_per_launch"]) if kernels else None)
     # DRAM traffic of the dominant kernel: from the committed ncu --set full capture of this round (a live
@@ -761,8 +769,10 @@ def run_gpu_arm(args):
             with open(os.path.join(ROOT, "profiles", cand)) as f:
                 tk = json.load(f)["kernels"]
             for name, v in tk.items():
-                if "k_frame_match" in name:
+                if dom_kernel in name:
                     traffic = v["dram_read_bytes"] + v["dram_write_bytes"]
+                    if seq_mode:   # captured with frames_per_launch frames in the launch: scale to this run's K
+                        traffic = traffic * K / v.get("frames_per_launch", K)
                     traffic_src = f"profiles/{cand}"
             if traffic is not None:
                 break
@@ -881,18 +891,24 @@ def run_gpu_arm(args):
                                       "api": "nav_frontend_frame (all four outputs, returns with the results on the host)",
                                       "wall_ms_per_step": 1e3 * blk_wall / n_block}},
             "e2e_closed_loop": closed, "e2e_shim": shim,
-            "gpu_launches": int(round(K)), "gpu_launches_note": "K launches of k_frame_match per timed repetition "
-                                                               "(%.0f launches per repetition including the untimed re-init "
-                                                               "and warm-up)" % launches_per_rep,
+            "gpu_launches": 1 if seq_mode else int(round(K)),
+            "gpu_launches_note": ("ONE launch of k_frame_seq covers the K timed steps of a repetition (a thread-block cluster "
+                                  "per image row walks through the frames; %.0f launches per repetition including the untimed "
+                                  "re-init and warm-up; NAV_SEQ_LAUNCHES=1 gives one k_frame_match launch per step)"
+                                  if seq_mode else
+                                  "K launches of k_frame_match per timed repetition (%.0f launches per repetition including the "
+                                  "untimed re-init and warm-up)") % launches_per_rep,
             "clocks": clk, "cpu_cores_bound_near_gpu": bound_cores,
             "roofline": None if dom is None else {
-                "kernel": {"frame_fused": "k_frame_match<fused labels, fused map>"}.get(dom, dom), "bound": "hbm",
+                "kernel": {"frame_fused": ("k_frame_seq (labels + match + next map, K frames per launch)" if seq_mode else
+                                           "k_frame_match<fused labels, fused map>")}.get(dom, dom), "bound": "hbm",
                 "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic,
                 "traffic_source": traffic_src,
                 "alg_bytes_per_launch": kernels[dom]["alg_bytes_per_launch"],
                 "us_per_launch": kernels[dom]["us_per_launch"],
-                "note": "one 3 MB frame per launch: bounded by instruction issue, not by HBM; "
+                "note": "3 MB per frame and a serial dependency from frame to frame: bounded by instruction issue and the "
+                        "latency chain of one image row, not by HBM; "
                         "the same stencil fed a batch reaches kernels.labels_batch.frac_of_hbm_peak"},
             "kernels": kernels, "batched_sequences": batched, "nn": nn, "cpu_baseline": cpu,
         }

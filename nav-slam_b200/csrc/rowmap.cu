@@ -217,6 +217,23 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
                  : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
+// tile_stage (stencil_tile.cuh) with asynchronous copies: columns [c0-2, c0+kTile+2) of one row into pts
+__device__ __forceinline__ void tile_stage_async(double *pts, const double *__restrict__ row_ptr, int c0, int cols) {
+    const int first = c0 - kHalo;
+    for (int i = threadIdx.x; i < kTilePts * 3; i += kTile) {
+        const int col = first + i / 3;
+        if (col >= 0 && col < cols)
+            cp_async8(&pts[i], row_ptr + (long long)first * 3 + i);
+        else
+            pts[i] = 0.0;
+    }
+}
 
 // the CTA's neighbourhood of the row map, prefetched into shared memory while the labels are
 // computed: its own 256 columns plus one 16-column leaf on each side (almost every query finds its
@@ -561,7 +578,8 @@ struct SeqArgs {
 __global__ void __launch_bounds__(kTile, NAV_MATCH_MIN_CTAS)
 k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, MatchOut out, int rows, int cols,
             unsigned *__restrict__ n_exact) {
-    __shared__ StencilSmem s;
+    __shared__ __align__(16) double s_pts[2][kTilePts * 3];  // the tile of this frame / of the next one (in flight)
+    __shared__ float s_f1[kTile + kHalo], s_f2[kTile + kHalo];
     __shared__ int s_warp[65];
     __shared__ int s_qcol[kTile];
     __shared__ MapSmem sm;
@@ -571,17 +589,24 @@ k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, Match
     const long long base = (long long)rid * cols;
     const int c0 = tile * kTile;
     const int c = c0 + threadIdx.x;
+    tile_stage_async(s_pts[0], a.frames + base * 3, c0, cols);
+    cp_async_commit();
     for (int f = 0; f < a.n_frames; ++f) {
-        const double *cloud = a.frames + (long long)f * a.frame_stride;
+        const double *pts = s_pts[f & 1];
         const RowMap &map = (f & 1) ? map1 : map0;
         const RowMap &map_next = (f & 1) ? map0 : map1;
         const RowView rv = {map.pts + base * 3, map.mask + (long long)rid * map.n_chunks,
                             map.box + (long long)rid * map.n_chunks * 2, map.sbox + (long long)rid * map.n_super * 2,
                             map.n_chunks, map.n_super, tile * kChunksPerSuper - 1};
         prefetch_neighbourhood<true>(sm, rv, cols);
-        tile_stage(s, cloud + base * 3, c0, cols);
+        cp_async_commit();
+        cp_async_wait_group<1>();  // this frame's tile (committed before the neighbourhood) has landed
         __syncthreads();
-        const int label = tile_labels_filtered(s, c0, cols, n_exact);
+        const int label = tile_labels_filtered(pts, s_f1, s_f2, c0, cols, n_exact);
+        // the next frame's tile starts its way from HBM now and has the whole search to arrive
+        if (f + 1 < a.n_frames)
+            tile_stage_async(s_pts[(f + 1) & 1], a.frames + (long long)(f + 1) * a.frame_stride + base * 3, c0, cols);
+        cp_async_commit();
         if (c < cols) {
             labels[base + c] = label;
             if (label != 1) {
@@ -592,7 +617,7 @@ k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, Match
         {
             P3 own = {0, 0, 0};
             if (c < cols) {
-                const double *sp = s.pts + (threadIdx.x + kHalo) * 3;
+                const double *sp = pts + (threadIdx.x + kHalo) * 3;
                 own.x = sp[0];
                 own.y = sp[1];
                 own.z = sp[2];
@@ -600,7 +625,7 @@ k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, Match
             map_tile(label == 1, c < cols, own, a.pose_fin[(long long)f * a.n_seq + seq], map_next, rid, tile, c, base,
                      s_lo, s_hi);
         }
-        cp_async_wait_all();
+        cp_async_wait_group<1>();  // the neighbourhood of the map; the next tile may still be in flight
         int nq;
         const int slot = block_excl_count(label == 1, s_warp, nq);  // its barriers also publish the prefetch
         if (label == 1) s_qcol[slot] = threadIdx.x;
@@ -608,7 +633,7 @@ k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, Match
         if ((int)(threadIdx.x & ~31u) < nq) {  // warps with at least one query; spare lanes repeat the last one
             const int t = s_qcol[min((int)threadIdx.x, nq - 1)];
             const int qc = c0 + t;
-            const double *sp = s.pts + (t + kHalo) * 3;
+            const double *sp = pts + (t + kHalo) * 3;
             const P3 p = {sp[0], sp[1], sp[2]};
             const PoseXf &pose = a.pose_loc[(long long)f * a.n_seq + seq];
             const P3 q = shift_point(pose, xf_point(pose, p));
