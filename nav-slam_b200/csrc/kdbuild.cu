@@ -64,8 +64,9 @@ struct KdSoA {
 struct SegBox {   // bounding box of a segment in key space
     u64 lo[3], hi[3];
 };
-struct SegPick {  // outcome of the histogram round of a large segment
-    int bin, below, count, pad;
+struct SegPick {  // outcome of the selection rounds of a large segment: the candidates' place and key range
+    int below, count, pad0, pad1;
+    u64 klo, khi;
 };
 struct SegSplit {
     int axis, shift;
@@ -228,10 +229,13 @@ k_kd_keys(const double *__restrict__ pts, int n, KdSoA out, SegBox *__restrict__
 }
 
 // box[0] = empty box; histogram row 0 and the counters of segment 0 = 0
-__global__ void k_kd_init(SegBox *box0, unsigned *ghist, unsigned *fill) {
+__global__ void k_kd_init(SegBox *box0, unsigned *ghist, unsigned *ghist2, unsigned *fill) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t == 0) box_reset(box0);
-    if (t < kBins) ghist[t] = 0u;
+    if (t < kBins) {
+        ghist[t] = 0u;
+        ghist2[t] = 0u;
+    }
     if (t < 4) fill[t] = 0u;
 }
 
@@ -595,6 +599,32 @@ __device__ __forceinline__ void emit_node(KdNode *nodes, int pos, const u64 key[
 }
 
 // ------------------------------------------------------------------------------------------------
+// Second selection round.  When the bin of the first round that holds the median is crowded (more than kCap
+// points: a thin slab of a wall or the floor, many points within a millimetre) the points of THAT bin are
+// binned again, by the next kBinBits key bits below `shift` -- or, if the bin is a single key value
+// (shift == 0), by the leading bits of the point index, the tie-breaker of the order.  Both are monotone in
+// (key, index), so "lower sub-bin" still means "smaller".
+struct Refine {
+    int on;        // 0: the first round's bin is the candidate set
+    int shift2;    // key refinement: sub-bin = (key - klo1) >> shift2
+    int by_id;     // index refinement: sub-bin = id >> id_shift
+    int id_shift;
+    u64 klo1;      // lowest key of the first round's bin
+};
+__device__ __forceinline__ Refine refine_of(const SegSplit &sp, int b1, int cnt1, int n) {
+    Refine r;
+    r.on = cnt1 > kCap;
+    r.klo1 = sp.base + ((u64)b1 << sp.shift);
+    r.by_id = sp.shift == 0;
+    r.shift2 = sp.shift > kBinBits ? sp.shift - kBinBits : 0;
+    const int id_bits = 32 - __clz(max(n - 1, 1));
+    r.id_shift = id_bits > kBinBits ? id_bits - kBinBits : 0;
+    return r;
+}
+__device__ __forceinline__ unsigned sub_bin(const Refine &r, u64 key, int id) {
+    return r.by_id ? (unsigned)id >> r.id_shift : (unsigned)((key - r.klo1) >> r.shift2);
+}
+
 // large segments, step 1: histogram of the split-axis keys.  grid = n_seg * cps CTAs.
 __global__ void __launch_bounds__(kPartThreads)
 k_kd_hist(KdSoA cur, int n, int level, int rule, int cps, const SegBox *__restrict__ box_cur,
@@ -634,11 +664,51 @@ k_kd_hist(KdSoA cur, int n, int level, int rule, int cps, const SegBox *__restri
         if (s_hist[t]) atomicAdd(&g[t], s_hist[t]);
 }
 
+// large segments, step 1b: histogram of the second round over the points of a crowded first-round bin.
+// Same grid as k_kd_hist; CTAs of segments whose bin is not crowded leave at once.
+__global__ void __launch_bounds__(kPartThreads)
+k_kd_hist2(KdSoA cur, int n, int level, int rule, int cps, const SegBox *__restrict__ box_cur,
+           const unsigned *__restrict__ ghist, unsigned *__restrict__ ghist2) {
+    __shared__ unsigned s_hist[kBins];
+    __shared__ int s_res[4];
+    __shared__ unsigned s_wsum[32];
+    const int s = blockIdx.x / cps, j = blockIdx.x % cps;
+    int lo, hi;
+    if (!segment_range(s, n, level, lo, hi)) return;
+    const int start = lo + j * kChunkElems;
+    if (start >= hi) return;
+    const int end = min(hi, start + kChunkElems);
+    const SegSplit sp = split_of(box_cur[s], level, rule);
+    int b1, below1, cnt1;
+    block_pick<kPartThreads>(ghist + (size_t)s * kBins, (hi - lo) >> 1, s_res, s_wsum, b1, below1, cnt1);
+    const Refine rf = refine_of(sp, b1, cnt1, n);
+    if (!rf.on) return;
+    for (int t = threadIdx.x; t < kBins; t += kPartThreads) s_hist[t] = 0u;
+    __syncthreads();
+    const u64 *ka = cur.k[sp.axis];
+    u64 kv[kPartItems];
+#pragma unroll
+    for (int it = 0; it < kPartItems; ++it) {
+        const int e = start + it * kPartThreads + threadIdx.x;
+        kv[it] = e < end ? ka[e] : 0ull;
+    }
+#pragma unroll
+    for (int it = 0; it < kPartItems; ++it) {
+        const int e = start + it * kPartThreads + threadIdx.x;
+        if (e < end && (int)((kv[it] - sp.base) >> sp.shift) == b1)
+            atomicAdd(&s_hist[sub_bin(rf, kv[it], rf.by_id ? cur.id[e] : 0)], 1u);
+    }
+    __syncthreads();
+    unsigned *g = ghist2 + (size_t)s * kBins;
+    for (int t = threadIdx.x; t < kBins; t += kPartThreads)
+        if (s_hist[t]) atomicAdd(&g[t], s_hist[t]);
+}
+
 // large segments, step 2: lower bins | candidates | higher bins.  Same grid as k_kd_hist.
 __global__ void __launch_bounds__(kPartThreads)
 k_kd_partition(KdSoA cur, KdSoA nxt, int n, int level, int rule, int cps, const SegBox *__restrict__ box_cur,
-               SegBox *__restrict__ box_next, const unsigned *__restrict__ ghist, unsigned *__restrict__ fill,
-               SegPick *__restrict__ pick) {
+               SegBox *__restrict__ box_next, const unsigned *__restrict__ ghist, const unsigned *__restrict__ ghist2,
+               unsigned *__restrict__ fill, SegPick *__restrict__ pick) {
     __shared__ int s_res[4];
     __shared__ unsigned s_wsum[32];
     __shared__ unsigned s_w[kPartThreads / 32][3];
@@ -651,13 +721,30 @@ k_kd_partition(KdSoA cur, KdSoA nxt, int n, int level, int rule, int cps, const 
     const int start = lo + j * kChunkElems;
     if (start >= hi) return;
     const int end = min(hi, start + kChunkElems);
-    const SegSplit sp = split_of(box_cur[s], level, rule);
+    const SegBox my_box = box_cur[s];
+    const SegSplit sp = split_of(my_box, level, rule);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 2) box_reset(&s_box[tid]);
     int b, below, cnt;
     block_pick<kPartThreads>(ghist + (size_t)s * kBins, (hi - lo) >> 1, s_res, s_wsum, b, below, cnt);
+    u64 klo, khi;
+    bin_range(sp, my_box.hi[sp.axis], b, klo, khi);
+    // crowded bin: the second round (k_kd_hist2) has binned its points again
+    const Refine rf = refine_of(sp, b, cnt, n);
+    int b2 = 0;
+    if (rf.on) {
+        int below2, cnt2;
+        block_pick<kPartThreads>(ghist2 + (size_t)s * kBins, ((hi - lo) >> 1) - below, s_res, s_wsum, b2, below2, cnt2);
+        below += below2;
+        cnt = cnt2;
+        if (!rf.by_id) {   // key range of the sub-bin (clipped to the first round's bin)
+            const u64 lo2 = rf.klo1 + ((u64)b2 << rf.shift2), span = (1ull << rf.shift2) - 1ull;
+            khi = (khi - lo2 > span) ? lo2 + span : khi;
+            klo = lo2;
+        }
+    }
     if (j == 0 && tid == 0) {
-        SegPick p = {b, below, cnt, 0};
+        SegPick p = {below, cnt, 0, 0, klo, khi};
         pick[s] = p;
     }
     // classify this CTA's points (2 bits each, kept in a register) and count the three categories
@@ -669,8 +756,13 @@ k_kd_partition(KdSoA cur, KdSoA nxt, int n, int level, int rule, int cps, const 
         const int e = start + it * kPartThreads + tid;
         unsigned cat = 3u;
         if (e < end) {
-            const int bin = (int)((ka[e] - sp.base) >> sp.shift);
+            const u64 key = ka[e];
+            const int bin = (int)((key - sp.base) >> sp.shift);
             cat = bin < b ? 0u : (bin > b ? 2u : 1u);
+            if (rf.on && cat == 1u) {
+                const int sb = (int)sub_bin(rf, key, rf.by_id ? cur.id[e] : 0);
+                cat = sb < b2 ? 0u : (sb > b2 ? 2u : 1u);
+            }
         }
         cats |= cat << (2 * it);
         nl += cat == 0u;
@@ -745,13 +837,17 @@ k_kd_partition(KdSoA cur, KdSoA nxt, int n, int level, int rule, int cps, const 
 __global__ void __launch_bounds__(kCtaThreads)
 k_kd_resolve(KdSoA out, KdSoA scratch, int n, int level, int rule, const SegBox *__restrict__ box_cur,
              SegBox *__restrict__ box_next, const SegPick *__restrict__ pick, unsigned *__restrict__ ghist,
-             unsigned *__restrict__ fill, int clear_next, KdNode *__restrict__ nodes, double *__restrict__ bbox_out) {
+             unsigned *__restrict__ ghist2, unsigned *__restrict__ fill, int clear_next, KdNode *__restrict__ nodes,
+             double *__restrict__ bbox_out) {
     extern __shared__ __align__(16) unsigned char kd_smem_raw[];
     KdSmem &sm = *reinterpret_cast<KdSmem *>(kd_smem_raw);
     const int s = blockIdx.x, tid = threadIdx.x;
     if (clear_next) {
-        unsigned *g = ghist + (size_t)(2 * s) * kBins;
-        for (int t = tid; t < 2 * kBins; t += kCtaThreads) g[t] = 0u;
+        unsigned *g = ghist + (size_t)(2 * s) * kBins, *g2 = ghist2 + (size_t)(2 * s) * kBins;
+        for (int t = tid; t < 2 * kBins; t += kCtaThreads) {
+            g[t] = 0u;
+            g2[t] = 0u;
+        }
     }
     if (tid < 8) fill[(size_t)(2 * s) * 4 + tid] = 0u;
     int lo, hi;
@@ -765,9 +861,7 @@ k_kd_resolve(KdSoA out, KdSoA scratch, int n, int level, int rule, const SegBox 
     if (tid < 2) box_reset(&sm.box[tid]);
     __syncthreads();
     const int m = (hi - lo) >> 1;
-    u64 klo, khi;
-    bin_range(sp, box_cur[s].hi[sp.axis], p.bin, klo, khi);
-    resolve_region<kCtaThreads>(sm, out, scratch, lo + p.below, p.count, m - p.below, sp.axis, klo, khi);
+    resolve_region<kCtaThreads>(sm, out, scratch, lo + p.below, p.count, m - p.below, sp.axis, p.klo, p.khi);
     if (tid == 0) emit_node(nodes, lo + m, sm.piv_key, sm.piv_id, sp.axis);
     if (tid < 6) {
         const int side = tid / 3, d = tid % 3;
@@ -1111,7 +1205,7 @@ cudaError_t kd_build(const double *d_pts, size_t n_sz, KdNode *d_nodes, double *
     KD_CHECK(kd_pool_alloc((void **)&keys, sizeof(u64) * n_sz * 6, device, stream));
     KD_CHECK(kd_pool_alloc((void **)&ids, sizeof(int) * n_sz * 2, device, stream));
     KD_CHECK(kd_pool_alloc((void **)&box, sizeof(SegBox) * seg_cap * 2 * 2, device, stream));
-    KD_CHECK(kd_pool_alloc((void **)&ghist, sizeof(unsigned) * kBins * hist_rows * 2, device, stream));
+    KD_CHECK(kd_pool_alloc((void **)&ghist, sizeof(unsigned) * kBins * hist_rows * 2 * 2, device, stream));  // both rounds
     KD_CHECK(kd_pool_alloc((void **)&fill, sizeof(unsigned) * 4 * hist_rows * 2 + 64, device, stream));
     KD_CHECK(kd_pool_alloc((void **)&pick, sizeof(SegPick) * hist_rows, device, stream));
     {
@@ -1122,7 +1216,8 @@ cudaError_t kd_build(const double *d_pts, size_t n_sz, KdNode *d_nodes, double *
         }
         SegBox *boxes[2] = {box, box + seg_cap * 2};
         int cur = 0;
-        k_kd_init<<<(kBins + 255) / 256, 256, 0, stream>>>(boxes[0], ghist, fill);
+        unsigned *ghist2 = ghist + (size_t)kBins * hist_rows * 2;
+        k_kd_init<<<(kBins + 255) / 256, 256, 0, stream>>>(boxes[0], ghist, ghist2, fill);
         int grid = (n + 255) / 256;
         if (grid > sm_count * 8) grid = sm_count * 8;
         k_kd_keys<<<grid, 256, 0, stream>>>(d_pts, n, buf[0], boxes[0]);
@@ -1135,12 +1230,13 @@ cudaError_t kd_build(const double *d_pts, size_t n_sz, KdNode *d_nodes, double *
                 const unsigned g = (unsigned)n_seg * (unsigned)cps;
                 k_kd_hist<<<g, kPartThreads, 0, stream>>>(buf[cur], n, level, split_rule, cps, boxes[cur], boxes[cur ^ 1],
                                                         ghist);
+                k_kd_hist2<<<g, kPartThreads, 0, stream>>>(buf[cur], n, level, split_rule, cps, boxes[cur], ghist, ghist2);
                 k_kd_partition<<<g, kPartThreads, 0, stream>>>(buf[cur], buf[cur ^ 1], n, level, split_rule, cps,
-                                                             boxes[cur], boxes[cur ^ 1], ghist, fill, pick);
+                                                             boxes[cur], boxes[cur ^ 1], ghist, ghist2, fill, pick);
                 k_kd_resolve<<<n_seg, kCtaThreads, sizeof(KdSmem), stream>>>(
-                    buf[cur ^ 1], buf[cur], n, level, split_rule, boxes[cur], boxes[cur ^ 1], pick, ghist, fill,
+                    buf[cur ^ 1], buf[cur], n, level, split_rule, boxes[cur], boxes[cur ^ 1], pick, ghist, ghist2, fill,
                     level + 1 < top_levels ? 1 : 0, d_nodes, d_bbox);
-                nl += 3;
+                nl += 4;
             } else {
                 k_kd_level_cta<<<n_seg, kCtaThreads, sizeof(KdSmem), stream>>>(buf[cur], buf[cur ^ 1], n, level, split_rule,
                                                                               boxes[cur], boxes[cur ^ 1], d_nodes, d_bbox);

@@ -13,8 +13,15 @@ nav = importlib.import_module("nav-slam_b200")
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
 s = stream.cuda_stream
-for n in [int(a) for a in sys.argv[1:]] or [65536, 1_000_000, 10_000_000]:
-    d_pts = torch.from_numpy(nav.synth.map_points(n, seed=n)).cuda()
+args = sys.argv[1:]
+for a in args or ["65536", "1000000", "10000000", "room"]:
+    if a == "room":   # config 4 as a SLAM run produces it: 8 mapped 64x2048 room frames (points on planes)
+        pts, _ = nav.synth.accumulated_map(8)
+        n = pts.shape[0]
+        d_pts = torch.from_numpy(pts).cuda()
+    else:
+        n = int(a)
+        d_pts = torch.from_numpy(nav.synth.map_points(n, seed=n)).cuda()
     for split in ("widest", "cyclic"):
         times = []
         for rep in range(8):
@@ -26,4 +33,5 @@ for n in [int(a) for a in sys.argv[1:]] or [65536, 1_000_000, 10_000_000]:
             times.append(e0.elapsed_time(e1))
             launches = t.launch_count()
             t.close()
-        print(f"n={n:9d} split={split:6s} build ms per call: " + " ".join(f"{x:6.2f}" for x in times) + f"   launches {launches}")
+        label = "room map" if a == "room" else f"n={n}"
+        print(f"{label:>12s} split={split:6s} build ms per call: " + " ".join(f"{x:6.2f}" for x in times) + f"   launches {launches}")
