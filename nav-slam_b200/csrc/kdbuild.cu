@@ -291,6 +291,7 @@ struct KdSmem {
     u64 K[3][kCap];
     int ID[kCap];
     unsigned hist[kBins];
+    unsigned hist2[kBins];
     unsigned short perm[kCap];
     unsigned short tmp[kCap];
     SegBox box[2];        // accumulated bounding boxes of the left / right half
@@ -337,19 +338,58 @@ __device__ __forceinline__ int pow2_at_least(int c) {
 
 // Argsort of c <= kBins elements by (key, index) in O(c): counting sort over kBins bins of the key range
 // [klo, khi] -- with about as many bins as elements a bin holds one or two of them on ordinary data -- and a
-// brute-force ranking inside each bin.  perm[0..c) receives the order; tmp is a scratch list, hist kBins words,
-// wsum 1 + T/32 words.  Returns false, leaving perm undefined, when some bin holds more than kBucketMax elements
-// (equal or nearly equal keys): the caller then takes the bitonic network.  Called by all T threads; the
-// result is CTA-uniform; ends with a barrier.
+// brute-force ranking inside each bin.  Lidar maps are not ordinary at every scale: a thin slab of wall points
+// plus a few far outliers puts hundreds of points into a dozen bins.  Then a SECOND level subdivides every bin
+// of the first histogram into as many equal key intervals as it holds points (so there are again about c
+// buckets in total, and the slab is resolved at its own scale) and the points are counted once more.
+// perm[0..c) receives the order; tmp is a scratch list, hist / hist2 kBins words each, wsum 1 + T/32 words.
+// Returns false, leaving perm undefined, when a bucket still holds more than kBucketMax elements (equal or
+// nearly equal keys): the caller then takes the bitonic network.  Called by all T threads; the result is
+// CTA-uniform; ends with a barrier.
 constexpr int kBucketMax = 48;
+
+// exclusive scan of h[0..kBins) in place (thread t owns kBins / T consecutive entries) and the largest entry.
+// wsum: 1 + T/32 words, wsum[0] receives the maximum.  Called by all T threads, ends with a barrier.
 template <int T>
-__device__ __forceinline__ bool counting_argsort(unsigned short *perm, unsigned short *tmp, unsigned *hist, unsigned *wsum,
-                                                 int c, const u64 *key, const int *id, u64 klo, u64 khi) {
+__device__ __forceinline__ void scan_bins(unsigned *h, unsigned *wsum) {
     constexpr int kPer = kBins / T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) wsum[0] = 0u;
+    unsigned cnt[kPer], run = 0, big = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        cnt[k] = h[kPer * tid + k];
+        run += cnt[k];
+        big = max(big, cnt[k]);
+    }
+    unsigned inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(kFullMask, inc, o);
+        if (lane >= o) inc += t;
+    }
+    big = __reduce_max_sync(kFullMask, big);
+    __syncthreads();  // wsum[0] is reset
+    if (lane == 31) wsum[1 + warp] = inc;
+    if (lane == 0) atomicMax(&wsum[0], big);
+    __syncthreads();
+    const unsigned before = lane < warp ? wsum[1 + lane] : 0u;  // T / 32 <= 32 warps
+    unsigned ex = __reduce_add_sync(kFullMask, before) + inc - run;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        h[kPer * tid + k] = ex;
+        ex += cnt[k];
+    }
+    __syncthreads();
+}
+
+template <int T>
+__device__ __forceinline__ bool counting_argsort(unsigned short *perm, unsigned short *tmp, unsigned *hist, unsigned *hist2,
+                                                 unsigned *wsum, int c, const u64 *key, const int *id, u64 klo, u64 khi) {
+    constexpr int kPer = kBins / T;
+    const int tid = threadIdx.x;
     const int shift = bin_shift(khi - klo);
     for (int i = tid; i < kBins; i += T) hist[i] = 0u;
-    if (tid == 0) wsum[0] = 0u;
     __syncthreads();
     unsigned bin[kPer], slot[kPer];
 #pragma unroll
@@ -363,48 +403,46 @@ __device__ __forceinline__ bool counting_argsort(unsigned short *perm, unsigned 
         }
     }
     __syncthreads();
-    {   // exclusive scan of the bin counts, in place; the fullest bin decides between fast path and fallback
-        unsigned cnt[kPer], run = 0, big = 0;
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            cnt[k] = hist[kPer * tid + k];
-            run += cnt[k];
-            big = max(big, cnt[k]);
-        }
-        unsigned inc = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(kFullMask, inc, o);
-            if (lane >= o) inc += t;
-        }
-        big = __reduce_max_sync(kFullMask, big);
-        if (lane == 31) wsum[1 + warp] = inc;
-        if (lane == 0 && big > (unsigned)kBucketMax) atomicMax(&wsum[0], big);
+    scan_bins<T>(hist, wsum);
+    const unsigned *start = hist;
+    if (wsum[0] > (unsigned)kBucketMax) {  // CTA-uniform
+        // second level: bin b with n_b points becomes n_b buckets start[b] .. start[b] + n_b - 1
+        for (int i = tid; i < kBins; i += T) hist2[i] = 0u;
         __syncthreads();
-        const unsigned before = lane < warp ? wsum[1 + lane] : 0u;  // T / 32 <= 32 warps
-        unsigned ex = __reduce_add_sync(kFullMask, before) + inc - run;
+        const u64 low_mask = shift ? ((1ull << shift) - 1ull) : 0ull;
+        const int pre = shift > 52 ? shift - 52 : 0;  // keeps (low >> pre) * n_b below 2^63
 #pragma unroll
         for (int k = 0; k < kPer; ++k) {
-            hist[kPer * tid + k] = ex;
-            ex += cnt[k];
+            const int i = tid + k * T;
+            if (i < c) {
+                const unsigned b = bin[k];
+                const unsigned bs = hist[b], nb = (b + 1 < (unsigned)kBins ? hist[b + 1] : (unsigned)c) - bs;
+                const u64 low = (key[i] - klo) & low_mask;
+                unsigned sub = (unsigned)(((low >> pre) * (u64)nb) >> (shift - pre));
+                sub = min(sub, nb - 1u);
+                bin[k] = bs + sub;
+                slot[k] = atomicAdd(&hist2[bin[k]], 1u);
+            }
         }
-    }
-    __syncthreads();
-    if (wsum[0] > (unsigned)kBucketMax) {
-        __syncthreads();  // everybody has read the flag before it can be reset by a following call
-        return false;
+        __syncthreads();
+        scan_bins<T>(hist2, wsum);
+        start = hist2;
+        if (wsum[0] > (unsigned)kBucketMax) {
+            __syncthreads();  // everybody has read the flag before a following call can reset it
+            return false;
+        }
     }
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
         const int i = tid + k * T;
-        if (i < c) tmp[hist[bin[k]] + slot[k]] = (unsigned short)i;
+        if (i < c) tmp[start[bin[k]] + slot[k]] = (unsigned short)i;
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
         const int i = tid + k * T;
         if (i >= c) continue;
-        const int bs = (int)hist[bin[k]], be = bin[k] + 1 < (unsigned)kBins ? (int)hist[bin[k] + 1] : c;
+        const int bs = (int)start[bin[k]], be = bin[k] + 1 < (unsigned)kBins ? (int)start[bin[k] + 1] : c;
         const u64 mine = key[i];
         const int my_id = id[i];
         int rank = 0;
@@ -438,7 +476,7 @@ __device__ void resolve_region(KdSmem &sm, const KdSoA &out, const KdSoA &scratc
             sm.ID[t] = out.id[a + t];
         }
         __syncthreads();
-        if (!counting_argsort<T>(sm.perm, sm.tmp, sm.hist, sm.wsum, c, sm.K[axis], sm.ID, klo, khi)) {
+        if (!counting_argsort<T>(sm.perm, sm.tmp, sm.hist, sm.hist2, sm.wsum, c, sm.K[axis], sm.ID, klo, khi)) {
             const int P = pow2_at_least(c);
             for (int t = tid; t < P; t += T) sm.perm[t] = t < c ? (unsigned short)t : (unsigned short)0xffffu;
             __syncthreads();
@@ -974,6 +1012,7 @@ struct FinSmem {
     int gid[kFinSeg];
     unsigned short lst[2][3][kFinSeg];
     unsigned sc[kFinSeg];           // exclusive prefix, lefts | medians << 16
+    unsigned sc2[kFinSeg];          // second-level bins of the counting sort
     unsigned char ax[kFinSeg];      // split axis of the node at a position
     unsigned char side[kFinSeg];    // left / median / right code per local id
     unsigned wsum[1 + kFinThreads / 32];
@@ -1016,7 +1055,7 @@ k_kd_finish(KdSoA in, int n, int level0, int rule, KdNode *__restrict__ nodes, d
     const SegBox sbox = box0[blockIdx.x];
     for (int d = 0; d < 3; ++d) {
         unsigned short *perm = sm.lst[0][d];
-        if (!counting_argsort<kFinThreads>(perm, sm.lst[1][d], sm.sc, sm.wsum, m, sm.K[d], sm.gid, sbox.lo[d], sbox.hi[d])) {
+        if (!counting_argsort<kFinThreads>(perm, sm.lst[1][d], sm.sc, sm.sc2, sm.wsum, m, sm.K[d], sm.gid, sbox.lo[d], sbox.hi[d])) {
             for (int i = tid; i < kFinSeg; i += kFinThreads) perm[i] = i < m ? (unsigned short)i : (unsigned short)0xffffu;
             __syncthreads();
             bitonic_argsort<kFinThreads>(perm, P, m, sm.K[d], sm.gid);
