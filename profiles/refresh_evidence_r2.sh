@@ -10,7 +10,7 @@ $BENCH > $O/bench_short.json 2> $O/bench_short.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/r2_launches_bench.csv $BENCH > $O/ncu_launch.log 2>&1
 python profiles/launch_summary.py $O/r2_launches_bench.csv "$BENCH" > $O/r2_launches_summary.txt
 # the dominant kernel of the timed region: one k_frame_seq launch = 20 frames
-ncu --set full --clock-control none --import-source on -k "regex:k_frame_seq" -s 6 -c 1 -f -o $O/r2_frame_seq $BENCH > $O/ncu_frame.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:k_frame_seq" -s 7 -c 1 -f -o $O/r2_frame_seq $BENCH > $O/ncu_frame.log 2>&1
 python profiles/ncu_table.py $O/r2_frame_seq.ncu-rep > $O/r2_frame_seq.txt 2>&1
 python profiles/ncu_kernels.py $O/r2_frame_seq.ncu-rep --json $O/r2_traffic.json --frames-per-launch 20 >> $O/r2_frame_seq.txt 2>&1
 # closed loop: the fused step kernel
