@@ -554,6 +554,8 @@ k_frame_match(const double *__restrict__ cloud, int *__restrict__ labels, RowMap
     out.nn_dist[base + qc] = bcol >= 0 ? __dsqrt_rn(best) : INFINITY;
 }
 
+__device__ __forceinline__ void cluster_arrive_all() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_all() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
 }
@@ -598,11 +600,15 @@ k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, Match
         const RowView rv = {map.pts + base * 3, map.mask + (long long)rid * map.n_chunks,
                             map.box + (long long)rid * map.n_chunks * 2, map.sbox + (long long)rid * map.n_super * 2,
                             map.n_chunks, map.n_super, tile * kChunksPerSuper - 1};
+        cp_async_wait_group<0>();  // this frame's tile has landed
+        __syncthreads();
+        // the labels need nothing from the row's other tiles: they are computed BEFORE waiting for the cluster
+        // (the barrier was only signalled at the end of the previous frame), which turns the wait for the row's
+        // slowest tile into useful time
+        const int label = tile_labels_filtered(pts, s_f1, s_f2, c0, cols, n_exact);
+        if (f > 0) cluster_wait_all();  // the row's map of the previous frame is complete (also a CTA barrier)
         prefetch_neighbourhood<true>(sm, rv, cols);
         cp_async_commit();
-        cp_async_wait_group<1>();  // this frame's tile (committed before the neighbourhood) has landed
-        __syncthreads();
-        const int label = tile_labels_filtered(pts, s_f1, s_f2, c0, cols, n_exact);
         // the next frame's tile starts its way from HBM now and has the whole search to arrive
         if (f + 1 < a.n_frames)
             tile_stage_async(s_pts[(f + 1) & 1], a.frames + (long long)(f + 1) * a.frame_stride + base * 3, c0, cols);
@@ -645,10 +651,11 @@ k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, Match
                 out.nn_dist[base + qc] = bcol >= 0 ? __dsqrt_rn(best) : INFINITY;
             }
         }
-        // the row's next map is complete and nobody of the row still reads the current one (also a CTA barrier:
-        // the shared-memory tiles are free for the next frame)
-        cluster_sync_all();
+        // this CTA's part of the row's next map is written and it no longer reads the current one: signal the
+        // cluster (release) and go on; the matching wait sits in front of the next frame's map prefetch
+        cluster_arrive_all();
     }
+    cluster_wait_all();  // every arrive has its wait
 }
 
 bool frame_seq_supported(int cols) { return div_up(cols, kTile) <= 8; }
