@@ -65,6 +65,18 @@ extern "C" int nav_device_count(void) {
     return n;
 }
 
+// pointers this thread has already seen to be pinned (Stager::is_pinned); nav_host_free / nav_host_unregister
+// forget theirs
+static const void **pinned_seen() {
+    static thread_local const void *seen[16] = {};
+    return seen;
+}
+static void pinned_forget(const void *p) {
+    const void **seen = pinned_seen();
+    for (int i = 0; i < 16; ++i)
+        if (seen[i] && seen[i] >= p) seen[i] = nullptr;  // conservatively: everything at or above the base address
+}
+
 extern "C" void *nav_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
@@ -74,7 +86,9 @@ extern "C" void *nav_host_alloc(size_t bytes) {
     return p;
 }
 extern "C" void nav_host_free(void *p) {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    pinned_forget(p);
+    cudaFreeHost(p);
 }
 // page-lock memory the caller already owns (cudaHostRegister), so that the host-buffer calls DMA it
 // directly instead of staging it through a bounce buffer
@@ -89,6 +103,7 @@ extern "C" int nav_host_register(void *p, size_t bytes) {
 }
 extern "C" int nav_host_unregister(void *p) {
     if (!p) return 0;
+    pinned_forget(p);
     if (cudaHostUnregister(p) != cudaSuccess) {
         cudaGetLastError();
         return fail("nav_host_unregister(%p) failed", p);
@@ -112,10 +127,10 @@ struct Stager {
     // same few buffers frame after frame, so pointers already seen to be pinned are remembered
     // (a buffer that stops being pinned would merely be copied through the driver's own staging)
     static bool is_pinned(const void *p) {
-        static thread_local const void *seen[16] = {};
+        const void **seen = pinned_seen();
         static thread_local unsigned next = 0;
-        for (const void *s : seen)
-            if (s == p) return true;
+        for (int i = 0; i < 16; ++i)
+            if (seen[i] == p) return true;
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
             cudaGetLastError();

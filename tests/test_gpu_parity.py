@@ -901,3 +901,50 @@ def test_closed_loop_with_prefetch_equals_blocking_loop(pkg, oracle, synth, shap
         last = a[f - 1][0]
     assert np.array_equal(ga, og)
     slam.close()
+
+
+@pytest.mark.gpu
+def test_slam_run_with_a_prediction_callback_and_registered_memory(pkg, synth):
+    """nav_slam_run driven by a caller's prediction callback (the EKF's place, src/main.c:303-306) on frames that
+    live in ordinary numpy memory page-locked with nav_host_register: same poses as the array-of-increments
+    form on torch-pinned memory; unpinned frames are refused."""
+    import ctypes as C
+    torch = pytest.importorskip("torch")
+    r, c, n = 16, 1800, 6
+    clouds = np.stack([synth.room_frame(r, c, f) for f in range(n)])
+    step = np.array([46.0, 2.0, -1.0, 0.0, 0.0, 0.0])
+    L = pkg.load_library()
+    binding = __import__("importlib").import_module("nav-slam_b200.binding")
+    NavPos = binding.NavPos
+    ctx = pkg.Context(r, c, device=0)
+    ctx.slam_init(np.zeros(6), clouds[0], want_global=False)
+    h = torch.from_numpy(clouds).pin_memory()
+    want, errs, ncs = ctx.slam_run([h[f].data_ptr() for f in range(1, n)], np.tile(step, (n - 1, 1)), np.zeros(6))
+    # the same through a callback, frames in registered numpy memory
+    own = clouds.copy()
+    assert L.nav_host_register(own.ctypes.data, own.nbytes) == 0
+    calls = []
+    PRED = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.POINTER(NavPos), C.POINTER(NavPos))
+
+    def predict(user, t, last, pred):
+        calls.append(t)
+        for k, name in enumerate(("x", "y", "z", "roll", "pitch", "yaw")):
+            setattr(pred[0], name, getattr(last[0], name) + step[k])
+    cb = PRED(predict)
+    ctx.slam_init(np.zeros(6), clouds[0], want_global=False)
+    ptrs = (C.c_void_p * (n - 1))(*[own[f].ctypes.data for f in range(1, n)])
+    out = (NavPos * (n - 1))()
+    start = NavPos(0, 0, 0, 0, 0, 0)
+    L.nav_slam_run.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, PRED, C.c_void_p, C.c_void_p,
+                               C.POINTER(NavPos), C.POINTER(NavPos), C.c_void_p, C.c_void_p]
+    rc = L.nav_slam_run(ctx.h, ptrs, n - 1, 0, cb, None, None, C.byref(start), out, None, None)
+    assert rc == 0, L.nav_last_error()
+    assert calls == list(range(n - 1))
+    got = np.array([[p.x, p.y, p.z, p.roll, p.pitch, p.yaw] for p in out])
+    assert np.array_equal(got, want)
+    assert L.nav_host_unregister(own.ctypes.data) == 0
+    # pageable frames: refused with a message, nothing queued
+    ctx.slam_init(np.zeros(6), clouds[0], want_global=False)
+    rc = L.nav_slam_run(ctx.h, ptrs, n - 1, 0, cb, None, None, C.byref(start), out, None, None)
+    assert rc != 0 and b"pinned" in L.nav_last_error()
+    ctx.close()

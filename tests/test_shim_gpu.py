@@ -12,6 +12,7 @@ from conftest import big_stack
 from oracle_lib import Pos, REF_DIR, RefLib, quiet_stdout, ref_available
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 class Shim:
@@ -159,3 +160,47 @@ def test_unmodified_main_l9_config2(synth, tmp_path):
     assert np.abs(a - b).max() <= 0.011
     same = (csv_ref == csv_shim)
     print("L9 CSV byte-identical:", same)
+
+
+@pytest.mark.gpu
+def test_shim_fast_modes_agree(synth, tmp_path):
+    """NAVSLAM_ADAM=stats with and without NAVSLAM_TRUST_FRAME / NAVSLAM_PIN (the shim page-locks the caller's
+    PointCloud and SLAM_attr where they lie): identical poses and identical mapped clouds.  The modes are read
+    once per process, so every combination runs in a process of its own."""
+    import json
+    import subprocess
+    import sys
+    code = r'''
+import importlib, json, sys, os
+import numpy as np
+sys.path.insert(0, %r)
+nav = importlib.import_module("nav-slam_b200")
+sb = importlib.import_module("nav-slam_b200.shim_binding")
+R, C_ = 16, 1800
+frames = nav.synth.room_sequence(R, C_, 4, cfg=2, elev=(-15.0, 15.0))
+shim = sb.ShimSlam(R, C_)
+pc = shim.pack_cloud(frames[0], ts=0)
+fd = os.dup(1); os.dup2(os.open(os.devnull, os.O_WRONLY), 1)
+shim.init_slam(np.zeros(6), pc)
+last = np.zeros(6); poses = []
+for f in range(1, 4):
+    pc[8:] = frames[f].reshape(-1).view(np.uint8)
+    p = shim.slam_localization(pc, last + np.array([48.0, 0.5, 0, 0, 0, 0]), last)
+    shim.slam_mapping(p, pc)
+    poses.append([float(v).hex() for v in p]); last = p
+g = shim.global_cloud(3).copy()
+os.dup2(fd, 1)
+print(json.dumps({"poses": poses, "sum": float(g.sum()).hex(), "fc": shim.frame_count}))
+shim.release()
+''' % ROOT
+    outs = {}
+    for name, env in (("stats", {"NAVSLAM_ADAM": "stats"}),
+                      ("trust", {"NAVSLAM_ADAM": "stats", "NAVSLAM_TRUST_FRAME": "1"}),
+                      ("pinned", {"NAVSLAM_ADAM": "stats", "NAVSLAM_TRUST_FRAME": "1", "NAVSLAM_PIN": "1"})):
+        e = {k: v for k, v in os.environ.items() if not k.startswith("NAVSLAM_")}
+        e.update(env)
+        res = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        outs[name] = json.loads(res.stdout.strip().splitlines()[-1])
+    assert outs["stats"] == outs["trust"] == outs["pinned"]
+    assert outs["stats"]["fc"] == 4   # init_slam + three mapped frames
