@@ -52,6 +52,29 @@ __device__ __forceinline__ double node_axis(const KdNode *__restrict__ nodes, in
 // Measured on B200 with the short-stack kernel, 131 072 queries: bucket 1 / 4 / 8 / 16 -> 107 / 98 / 88 / 98 us
 // on 1 M uniform points, 169 / 148 / 138 / 162 us on the accumulated room map.
 constexpr int kKdBucket = 8;
+// the same run with all (<= kKdBucket) node loads issued before the first distance is formed: one memory
+// latency per run instead of one per node (the loop below waits for every node in turn)
+__device__ __forceinline__ void scan_run_batched(const KdNode *__restrict__ nodes, int lo, int hi, double qx, double qy,
+                                                 double qz, double &best, int &bidx) {
+    double2 a[kKdBucket], b[kKdBucket];
+#pragma unroll
+    for (int k = 0; k < kKdBucket; ++k) {
+        const int i = min(lo + k, hi - 1);  // a short run repeats its last node, which the compare ignores
+        const double2 *p = reinterpret_cast<const double2 *>(nodes + i);
+        a[k] = __ldg(p);
+        b[k] = __ldg(p + 1);
+    }
+#pragma unroll
+    for (int k = 0; k < kKdBucket; ++k) {
+        const int idx = (int)(__double_as_longlong(b[k].y) & 0xffffffffll);
+        const double d = dsq3(dsub(a[k].x, qx), dsub(a[k].y, qy), dsub(b[k].x, qz));
+        if (d < best || (d == best && idx < bidx)) {
+            best = d;
+            bidx = idx;
+        }
+    }
+}
+
 __device__ __forceinline__ void scan_run(const KdNode *__restrict__ nodes, int lo, int hi, double qx, double qy,
                                          double qz, double &best, int &bidx) {
     for (int i = lo; i < hi; ++i) {
@@ -299,7 +322,7 @@ k_kd_nn_stack(const KdNode *__restrict__ nodes, int n, const double *__restrict_
     while (true) {
         while (lo < hi) {
             if (hi - lo <= kKdBucket) {
-                scan_run(nodes, lo, hi, qx, qy, qz, best, bidx);
+                scan_run_batched(nodes, lo, hi, qx, qy, qz, best, bidx);
                 break;
             }
             const int mid = lo + ((hi - lo) >> 1);
