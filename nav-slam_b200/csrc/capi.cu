@@ -1516,6 +1516,23 @@ extern "C" int nav_frontend_sequence_dev(nav_ctx *c, const void *dev_frames, siz
     static const bool per_frame = getenv("NAV_SEQ_LAUNCHES") != nullptr;
     if (!per_frame && !c->prof && c->n_seq == 1 && n_frames > 1 && frame_seq_supported(c->cols) && n_frames <= 0x7fffffff) {
         const size_t n_pose = n_frames * (size_t)c->n_seq, bytes = n_pose * 2 * sizeof(PoseXf);
+        const MatchOut out = {c->d_nn_idx, c->d_nn_dist, c->d_corr_rows, c->d_corr_row_count};
+        if ((int)n_frames <= frame_seq_inline_frames()) {  // short sequence: poses as kernel parameters
+            PoseXf loc[64], fin[64];
+            static_assert(sizeof(loc) / sizeof(loc[0]) >= 64, "");
+            if (frame_seq_inline_frames() > 64) return fail("nav_frontend_sequence_dev: inline pose capacity");
+            for (size_t i = 0; i < n_pose; ++i) {
+                loc[i] = make_pose(&pos_predict[i], &pos_last[i]);
+                fin[i] = make_pose(&pos_final[i], nullptr);
+            }
+            CU((cudaError_t)launch_frame_seq(base, (long long)c->ntot * 3, (int)n_frames, c->d_labels, c->map, c->map_alt, out,
+                                             nullptr, nullptr, c->n_seq, c->rows, c->cols, c->d_n_exact, c->stream, loc, fin));
+            c->launches++;
+            if (n_frames & 1) std::swap(c->map, c->map_alt);
+            c->cloud_resident = false;
+            CU(cudaGetLastError());
+            return 0;
+        }
         nav_ctx::PoseRing &pr = c->pose_ring[c->pose_ring_next];
         c->pose_ring_next = (c->pose_ring_next + 1) % nav_ctx::kPoseRing;
         if (pr.done) CU(cudaEventSynchronize(pr.done));  // the staging buffer's previous upload (several sequences ago)
@@ -1542,7 +1559,6 @@ extern "C" int nav_frontend_sequence_dev(nav_ctx *c, const void *dev_frames, siz
         }
         CU(cudaMemcpyAsync(c->d_pose, pr.host, bytes, cudaMemcpyHostToDevice, c->stream));
         CU(cudaEventRecord(pr.done, c->stream));
-        const MatchOut out = {c->d_nn_idx, c->d_nn_dist, c->d_corr_rows, c->d_corr_row_count};
         CU((cudaError_t)launch_frame_seq(base, (long long)c->ntot * 3, (int)n_frames, c->d_labels, c->map, c->map_alt, out,
                                          (const PoseXf *)c->d_pose, (const PoseXf *)c->d_pose + n_pose, c->n_seq, c->rows,
                                          c->cols, c->d_n_exact, c->stream));

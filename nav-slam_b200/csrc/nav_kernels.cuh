@@ -43,9 +43,11 @@ struct FitMailbox {
 // through the frames); map0 is searched by frame 0, frame f builds the map for frame f+1 in the other buffer.
 // d_pose_loc / d_pose_fin: device arrays [n_frames][n_seq].  Needs frame_seq_supported(cols).
 bool frame_seq_supported(int cols);
+int frame_seq_inline_frames();  // sequences up to this length (one sequence) carry their poses as kernel parameters
 int launch_frame_seq(const double *frames, long long frame_stride, int n_frames, int *labels, const RowMap &map0,
                      const RowMap &map1, const MatchOut &out, const PoseXf *d_pose_loc, const PoseXf *d_pose_fin,
-                     int n_seq, int rows, int cols, unsigned *n_exact, cudaStream_t stream);
+                     int n_seq, int rows, int cols, unsigned *n_exact, cudaStream_t stream,
+                     const PoseXf *h_pose_loc = nullptr, const PoseXf *h_pose_fin = nullptr);
 
 size_t dedupe_smem_bytes(int cols);
 int configure_row_kernels(int cols);  // opt in to large dynamic shared memory; 0 on success

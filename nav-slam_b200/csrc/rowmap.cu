@@ -569,6 +569,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 // labels (a3), query transform (a7), exact search of the row map of the previous frame (a6), the next map from
 // the frame's final pose into the other map buffer (a7, a4/a5).  labels / nn_idx / nn_dist hold the results of
 // the last frame, as after the same number of separate launches.
+constexpr int kSeqInlineFrames = 64;
 struct SeqArgs {
     const double *frames;     // [n_frames][n_seq*rows][cols][3]
     long long frame_stride;   // doubles between consecutive frames
@@ -576,10 +577,17 @@ struct SeqArgs {
     const PoseXf *pose_loc;   // [n_frames][n_seq] predicted pose + shift (queries)
     const PoseXf *pose_fin;   // [n_frames][n_seq] final pose (map)
 };
+// poses of a short sequence travel as kernel parameters (CUDA 12.1+: up to 32 764 bytes): no upload to queue
+// in front of the launch, no staging buffer to guard
+struct SeqInlinePoses {
+    PoseXf loc[kSeqInlineFrames], fin[kSeqInlineFrames];
+};
+static_assert(sizeof(SeqInlinePoses) + 256 < 32764, "inline poses must fit the kernel parameter space");
 
+template <bool kInline>
 __global__ void __launch_bounds__(kTile, NAV_MATCH_MIN_CTAS)
 k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, MatchOut out, int rows, int cols,
-            unsigned *__restrict__ n_exact) {
+            unsigned *__restrict__ n_exact, const __grid_constant__ SeqInlinePoses ip) {
     __shared__ __align__(16) double s_pts[2][kTilePts * 3];  // the tile of this frame / of the next one (in flight)
     __shared__ float s_f1[kTile + kHalo], s_f2[kTile + kHalo];
     __shared__ int s_warp[65];
@@ -628,8 +636,8 @@ k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, Match
                 own.y = sp[1];
                 own.z = sp[2];
             }
-            map_tile(label == 1, c < cols, own, a.pose_fin[(long long)f * a.n_seq + seq], map_next, rid, tile, c, base,
-                     s_lo, s_hi);
+            map_tile(label == 1, c < cols, own, kInline ? ip.fin[f] : a.pose_fin[(long long)f * a.n_seq + seq], map_next, rid,
+                     tile, c, base, s_lo, s_hi);
         }
         cp_async_wait_group<1>();  // the neighbourhood of the map; the next tile may still be in flight
         int nq;
@@ -641,7 +649,7 @@ k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, Match
             const int qc = c0 + t;
             const double *sp = pts + (t + kHalo) * 3;
             const P3 p = {sp[0], sp[1], sp[2]};
-            const PoseXf &pose = a.pose_loc[(long long)f * a.n_seq + seq];
+            const PoseXf &pose = kInline ? ip.loc[f] : a.pose_loc[(long long)f * a.n_seq + seq];
             const P3 q = shift_point(pose, xf_point(pose, p));
             double best;
             int bcol;
@@ -660,11 +668,18 @@ k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, Match
 
 bool frame_seq_supported(int cols) { return div_up(cols, kTile) <= 8; }
 
+int frame_seq_inline_frames() { return kSeqInlineFrames; }
+
+// h_pose_loc / h_pose_fin != null (n_seq == 1, n_frames <= frame_seq_inline_frames()): the poses are passed as
+// kernel parameters and the device arrays are not read
 int launch_frame_seq(const double *frames, long long frame_stride, int n_frames, int *labels, const RowMap &map0,
                      const RowMap &map1, const MatchOut &out, const PoseXf *d_pose_loc, const PoseXf *d_pose_fin,
-                     int n_seq, int rows, int cols, unsigned *n_exact, cudaStream_t stream) {
+                     int n_seq, int rows, int cols, unsigned *n_exact, cudaStream_t stream, const PoseXf *h_pose_loc,
+                     const PoseXf *h_pose_fin) {
     const int tiles = div_up(cols, kTile);
     const SeqArgs a = {frames, frame_stride, n_frames, n_seq, d_pose_loc, d_pose_fin};
+    const bool inl = h_pose_loc && h_pose_fin && n_seq == 1 && n_frames <= kSeqInlineFrames;
+
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)tiles, (unsigned)rows, (unsigned)n_seq);
     cfg.blockDim = dim3(kTile);
@@ -676,7 +691,17 @@ int launch_frame_seq(const double *frames, long long frame_stride, int n_frames,
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, k_frame_seq, a, labels, map0, map1, out, rows, cols, n_exact);
+    if (inl) {
+        SeqInlinePoses ip;  // the launch copies its parameters at the call
+        for (int f = 0; f < n_frames; ++f) {
+            ip.loc[f] = h_pose_loc[f];
+            ip.fin[f] = h_pose_fin[f];
+        }
+        for (int f = n_frames; f < kSeqInlineFrames; ++f) ip.loc[f] = ip.fin[f] = h_pose_loc[0];
+        return (int)cudaLaunchKernelEx(&cfg, k_frame_seq<true>, a, labels, map0, map1, out, rows, cols, n_exact, ip);
+    }
+    static const SeqInlinePoses none = {};
+    return (int)cudaLaunchKernelEx(&cfg, k_frame_seq<false>, a, labels, map0, map1, out, rows, cols, n_exact, none);
 }
 
 void launch_frame_map(const double *cloud, const int *labels, const RowMap &map, const PoseBatch &poses,
