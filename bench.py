@@ -577,15 +577,17 @@ def run_gpu_arm(args):
             if key not in ios:
                 o = out_ptrs(i & 1)
                 io = NavFrameIO()
-                if kind == "depth_masks":
+                if kind in ("depth_masks", "depth_masks_idx"):
                     io.distances = h_depth.data_ptr() + (cur % n_depth) * NPX * 4
                 else:
                     io.cloud = h_base + cur * FRAME_BYTES
-                if kind in ("masks", "depth_masks"):
+                if kind in ("masks", "depth_masks", "depth_masks_idx"):
                     io.mask_out = o["mask"]
                 else:
                     io.feature_out = o["feature"]
-                io.nn_idx_out, io.nn_dist_out = o["idx"], o["dist"]
+                io.nn_idx_out = o["idx"]
+                if kind != "depth_masks_idx":
+                    io.nn_dist_out = o["dist"]
                 if kind == "all_outputs":
                     io.global_out = o["global"]
                 ios[key] = io
@@ -632,6 +634,7 @@ def run_gpu_arm(args):
     e2e_labels = e2e_leg("labels")
     e2e_all = e2e_leg("all_outputs")
     e2e_depth = e2e_leg("depth_masks")
+    e2e_depth_idx = e2e_leg("depth_masks_idx")
     n_block = max(K, 50)
     blk_wall = timed_wall(blocking_step, n_block, None)
 
@@ -887,6 +890,11 @@ def run_gpu_arm(args):
                                     "api": "nav_frontend_submit(distances, mask_out, nn_idx_out, nn_dist_out): L5-type depth "
                                            "matrix in (utils/pointcloud.c:8 runs on the device)",
                                     "h2d_bytes_per_step": NPX * 4, "d2h_bytes_per_step": NPX * 12 + ROWS * n_chunks * 4},
+                    "depth_input_idx_only": {**e2e_depth_idx,
+                                             "api": "same with nn_dist_out = NULL: label masks + NN indices come back (the "
+                                                    "smallest per-pixel result; what still scales when eight ranks share the "
+                                                    "host's PCIe fabric)",
+                                             "h2d_bytes_per_step": NPX * 4, "d2h_bytes_per_step": NPX * 4 + ROWS * n_chunks * 4},
                     "blocking_call": {"value": world * n_block / blk_wall, "unit": "frames/s",
                                       "api": "nav_frontend_frame (all four outputs, returns with the results on the host)",
                                       "wall_ms_per_step": 1e3 * blk_wall / n_block}},
