@@ -978,10 +978,32 @@ def kd_legs(args, torch, dist, pkg, stream, world, rank, local, spin_up, barrier
     q_ms = time_steps(lambda: sharding.sharded_nn_into(nn_into, d_q, buf_i, buf_d))
     matched = int((buf_i >= 0).sum())
     q_ms, b_ms = reduce_max([q_ms, b_ms])
+    # the same exchange over peer memory: the search kernel stores its shard's answers into the buffers of all ranks
+    # (CUDA IPC mappings, NVLink stores) and no collective follows (nav_kdtree_nn_allgather_dev)
+    peer, peer_ms, peer_same, peer_err = None, None, None, None
+    if world > 1:
+        try:
+            peer = sharding.PeerGather(pkg.load_library(), local, nq * world)   # sized for the weak-scaling run too
+            peer.nq = nq
+            pi, pd = peer.nn(tree, d_q, s)
+            torch.cuda.synchronize()
+            peer_same = bool(torch.equal(pi[:nq], buf_i) and torch.equal(pd[:nq], buf_d))
+            peer_ms = reduce_max([time_steps(lambda: peer.nn(tree, d_q, s))])[0]
+            peer.check()
+        except Exception as ex:  # noqa: BLE001
+            peer_err = str(ex)[:200]
+            if peer is not None:
+                peer.close()
+            peer = None
     nn = {"workload": ("cfg5b: 10 M-point map replicated, 131072 queries sharded over %d ranks + one packed all_gather" % world)
           if world > 1 else ("cfg4: %d-point map, 131072 queries" % n_map),
           "map_points": n_map, "queries": nq, "build_ms": b_ms, "build_launches": b_launches, "query_ms": q_ms,
           "queries_per_s": nq / (q_ms * 1e-3), "matched": matched,
+          "peer_memory": None if world == 1 else (
+              {"error": peer_err} if peer_ms is None else
+              {"exchange": "no collective: the search kernel stores its shard's answers into every rank's buffer over "
+                           "NVLink (CUDA IPC mappings) and posts a flag; a one-warp kernel waits for the flags",
+               "query_ms": peer_ms, "queries_per_s": nq / (peer_ms * 1e-3), "same_answers_as_all_gather": peer_same}),
           "roofline_query": {"kernel": "k_kd_nn_stack", "bound": "hbm (latency-bound traversal; tree bytes are cache traffic)",
                              "alg_bytes_per_launch": nq * 36 // world, "achieved": nq * 36 / (q_ms * 1e-3) / 1e9,
                              "peak": peak, "unit": "GB/s", "frac": nq * 36 / (q_ms * 1e-3) / 1e9 / peak},
@@ -998,7 +1020,19 @@ def kd_legs(args, torch, dist, pkg, stream, world, rank, local, spin_up, barrier
         w_ms = reduce_max([time_steps(lambda: sharding.sharded_nn_into(nn_into, d_qw, wi, wd))])[0]
         nn["weak_scaling"] = {"queries_total": nq_w, "queries_per_rank": nq, "query_ms": w_ms,
                               "queries_per_s": nq_w / (w_ms * 1e-3)}
+        if peer is not None:
+            try:
+                peer.nq = nq_w
+                wp_ms = reduce_max([time_steps(lambda: peer.nn(tree, d_qw, s))])[0]
+                peer.check()
+                nn["weak_scaling"]["peer_memory_query_ms"] = wp_ms
+                nn["weak_scaling"]["peer_memory_queries_per_s"] = nq_w / (wp_ms * 1e-3)
+            except Exception as ex:  # noqa: BLE001
+                nn["weak_scaling"]["peer_memory_error"] = str(ex)[:200]
         del d_qw, wi, wd
+    if peer is not None:
+        barrier()
+        peer.close()
     tree.close()
     del d_pts
     if world == 1 and not args.big_map:

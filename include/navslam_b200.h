@@ -105,6 +105,23 @@ int nav_kdtree_nn_batch(nav_kdtree *tree, const nav_point *queries, size_t nq,
                         int32_t *idx_out, double *dist_out, nav_point *nearest_out);
 int nav_kdtree_nn_batch_dev(nav_kdtree *tree, const void *dev_queries, size_t nq,
                             void *dev_idx_out, void *dev_dist_out, void *cuda_stream);
+
+/* ---- config 5b over peer memory ------------------------------------------------------------------
+ * Queries sharded across the GPUs of one node against a replicated tree (BASELINE config 5): every rank's search
+ * kernel stores its shard's answers directly into the result buffers of all ranks (CUDA IPC mappings, NVLink
+ * stores) -- the all-gather is the kernel's epilogue, no collective follows.  One process per GPU:
+ *   p = nav_peer_create(device, nq_total, my_handle);            exchange the 64-byte handles (any transport)
+ *   nav_peer_connect(p, world, rank, all_handles);
+ *   nav_kdtree_nn_allgather_dev(tree, p, my_queries, q_lo, n_mine, &idx, &dist, stream);   per frame
+ * idx / dist (device pointers into this rank's buffer) hold the answers of ALL queries once the stream has
+ * passed the call; they stay valid until the call after the next one.  world <= 8. */
+typedef struct nav_peer nav_peer;
+nav_peer *nav_peer_create(int device, size_t nq_total, unsigned char handle_out[64]);
+int nav_peer_connect(nav_peer *p, int world, int rank, const unsigned char *handles /* world x 64 bytes */);
+int nav_kdtree_nn_allgather_dev(nav_kdtree *tree, nav_peer *p, const void *dev_queries, size_t q_lo, size_t nq_shard,
+                                void **idx_full, void **dist_full, void *cuda_stream);
+int nav_peer_check(nav_peer *p);   /* after a synchronisation: did every rank deliver every call? */
+void nav_peer_destroy(nav_peer *p);
 /* exact brute force on the same contract.  use_tensor_cores == 0: plain binary64 scan.
  * use_tensor_cores != 0: tcgen05 candidate tiles (bf16 hi/mid/lo splits, fp32 accumulate in TMEM) flag
  * every 32-point group that can contain the nearest neighbour, then an exact binary64 re-rank of the

@@ -55,6 +55,7 @@ EXPORTS = [
     "nav_csv_format_frame_dev", "nav_l5_json_read", "nav_imu_json_read",
     "nav_frontend_submit", "nav_frontend_frame_depth_async", "nav_slam_prefetch", "nav_slam_prefetch_depth",
     "nav_host_register", "nav_host_unregister", "nav_slam_run",
+    "nav_peer_create", "nav_peer_connect", "nav_kdtree_nn_allgather_dev", "nav_peer_check", "nav_peer_destroy",
 ]
 
 
@@ -131,6 +132,13 @@ def load_library(build_if_missing: bool = True):
                                                  vp, vp, vp, vp, vp]
     L.nav_slam_run.argtypes = [vp, C.POINTER(C.c_void_p), C.c_int, C.c_int, vp, vp, C.POINTER(NavPos),
                                C.POINTER(NavPos), C.POINTER(NavPos), C.POINTER(C.c_double), C.POINTER(C.c_size_t)]
+    L.nav_peer_create.restype = C.c_void_p
+    L.nav_peer_create.argtypes = [C.c_int, C.c_size_t, C.c_char_p]
+    L.nav_peer_connect.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.nav_kdtree_nn_allgather_dev.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_void_p), vp]
+    L.nav_peer_check.argtypes = [vp]
+    L.nav_peer_destroy.argtypes = [vp]
     L.nav_slam_prefetch.argtypes = [vp, vp]
     L.nav_slam_prefetch_depth.argtypes = [vp, vp]
     L.nav_l9_csv_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_size_t, vp, vp, C.POINTER(C.c_size_t)]

@@ -1774,6 +1774,133 @@ extern "C" int nav_kdtree_nn_batch_dev(nav_kdtree *t, const void *dev_queries, s
     return 0;
 }
 
+// ------------------------------------------------------------------ peer-memory exchange -----
+// Config 5b (queries sharded across the GPUs of a node against a replicated tree): instead of a collective
+// behind the search, every rank's search kernel writes its shard's answers straight into the result buffers of
+// ALL ranks (CUDA IPC mappings of each other's memory, NVLink / NVSwitch stores) and posts a flag; a one-warp
+// kernel on each rank waits for the eight flags.  Buffers are double-buffered by call parity: a rank can be at
+// most one call ahead of the slowest one, because it needs everybody's flag of call k before it starts k + 1.
+struct nav_peer {
+    int device = 0, world = 1, rank = 0;
+    size_t nq_cap = 0, half = 0;
+    unsigned char *own = nullptr;
+    unsigned char *peer[kMaxPeers] = {};
+    bool opened[kMaxPeers] = {};
+    unsigned long long seq = 0;
+};
+
+static size_t peer_half_bytes(size_t nq_cap) { return nq_cap * 12 + kMaxPeers * 8; }
+
+extern "C" void nav_peer_destroy(nav_peer *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (p->opened[r]) cudaIpcCloseMemHandle(p->peer[r]);
+    if (p->own) cudaFree(p->own);
+    delete p;
+}
+
+extern "C" nav_peer *nav_peer_create(int device, size_t nq_cap, unsigned char handle_out[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the handle is exchanged as 64 bytes");
+    if (!handle_out || nq_cap == 0) {
+        fail("nav_peer_create: null argument");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        fail("nav_peer_create: cudaSetDevice(%d) failed", device);
+        return nullptr;
+    }
+    nav_peer *p = new nav_peer();
+    p->device = device;
+    p->nq_cap = (nq_cap + 1) & ~(size_t)1;
+    p->half = peer_half_bytes(p->nq_cap);
+    const size_t bytes = 2 * p->half + 64;
+    cudaIpcMemHandle_t h;
+    if (cudaMalloc((void **)&p->own, bytes) != cudaSuccess || cudaMemset(p->own, 0, bytes) != cudaSuccess ||
+        cudaIpcGetMemHandle(&h, p->own) != cudaSuccess) {
+        fail("nav_peer_create: %s", cudaGetErrorString(cudaGetLastError()));
+        nav_peer_destroy(p);
+        return nullptr;
+    }
+    memcpy(handle_out, &h, 64);
+    return p;
+}
+
+// handles: world x 64 bytes, in rank order (this rank's own entry is ignored)
+extern "C" int nav_peer_connect(nav_peer *p, int world, int rank, const unsigned char *handles) {
+    if (!p || !handles) return fail("nav_peer_connect: null argument");
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail("nav_peer_connect: bad world %d / rank %d", world, rank);
+    CU(cudaSetDevice(p->device));
+    p->world = world;
+    p->rank = rank;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            p->peer[r] = p->own;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * 64, 64);
+        void *ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail("nav_peer_connect: cannot map the buffer of rank %d: %s", r, cudaGetErrorString(e));
+        }
+        p->peer[r] = (unsigned char *)ptr;
+        p->opened[r] = true;
+    }
+    return 0;
+}
+
+// Answers this rank's shard (nq_shard queries at dev_queries, queries q_lo .. q_lo + nq_shard - 1 of the whole
+// set) and delivers it to every rank; when the stream reaches the end of this call the full (idx, dist) arrays
+// of ALL ranks' shards are complete in this rank's buffer: *idx_full / *dist_full point at them (valid until
+// the call after the next one).
+extern "C" int nav_kdtree_nn_allgather_dev(nav_kdtree *t, nav_peer *p, const void *dev_queries, size_t q_lo,
+                                           size_t nq_shard, void **idx_full, void **dist_full, void *cuda_stream) {
+    if (!t || !p || !idx_full || !dist_full) return fail("nav_kdtree_nn_allgather_dev: null argument");
+    if (nq_shard && !dev_queries) return fail("nav_kdtree_nn_allgather_dev: null queries");
+    if (q_lo + nq_shard > p->nq_cap) return fail("nav_kdtree_nn_allgather_dev: shard exceeds the buffer (%zu)", p->nq_cap);
+    if (t->device != p->device) return fail("nav_kdtree_nn_allgather_dev: tree and buffer live on different devices");
+    CU(cudaSetDevice(t->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    if (t->on_user_stream && t->user_stream != s) CU(cudaStreamSynchronize(t->user_stream));
+    t->user_stream = s;
+    t->on_user_stream = true;
+    const unsigned long long seq = ++p->seq;
+    const size_t off = (seq & 1ull) * p->half;
+    KdFanOut fan = {};
+    for (int r = 0; r < p->world; ++r) {
+        unsigned char *b = p->peer[r] + off;
+        fan.dist[r] = (double *)b;
+        fan.idx[r] = (int *)(b + p->nq_cap * 8);
+        fan.flags[r] = (unsigned long long *)(b + p->nq_cap * 12);
+    }
+    fan.ticket = (unsigned *)(p->own + 2 * p->half);
+    fan.q_lo = (long long)q_lo;
+    fan.seq = seq;
+    fan.world = p->world;
+    fan.rank = p->rank;
+    CU(kd_nn_fanout(t->d_nodes, t->n, (const double *)dev_queries, nq_shard, fan, s, &t->launches));
+    CU(peer_wait((const unsigned long long *)(p->own + off + p->nq_cap * 12), p->world, seq,
+                 (unsigned *)(p->own + 2 * p->half + 4), s));
+    t->launches++;
+    *dist_full = p->own + off;
+    *idx_full = p->own + off + p->nq_cap * 8;
+    return 0;
+}
+
+// after a synchronisation: 0 if every wait so far saw all ranks arrive, else an error naming the first missing rank
+extern "C" int nav_peer_check(nav_peer *p) {
+    if (!p) return fail("nav_peer_check: null argument");
+    CU(cudaSetDevice(p->device));
+    unsigned err = 0;
+    CU(cudaMemcpy(&err, p->own + 2 * p->half + 4, 4, cudaMemcpyDeviceToHost));
+    if (err) return fail("nav_peer: rank %u did not deliver within 5 s", err - 1u);
+    return 0;
+}
+
 extern "C" int nav_kdtree_nn_batch(nav_kdtree *t, const nav_point *queries, size_t nq, int32_t *idx_out,
                                    double *dist_out, nav_point *nearest_out) {
     if (!t) return fail("nav_kdtree_nn_batch: null tree");

@@ -301,20 +301,22 @@ k_kd_nn_conv(const KdNode *__restrict__ nodes, int n, const double *__restrict__
 // (Tried on top of this: the incremental per-axis cell bound of Arya & Mount, offsets stacked as
 // floats rounded toward zero.  Exact, but 10-15 % slower on every map measured -- the plane test
 // already rejects nearly everything the stronger bound would; profiles/README.md.)
+// kFanOut: the answers of this rank's query shard are written straight into the result buffers of EVERY rank
+// (peer memory over NVLink; nav_kdtree_nn_allgather_dev) -- the all-gather is the kernel's epilogue --, and
+// the CTA that finishes last posts this rank's arrival in every rank's flag slot.
+template <bool kFanOut>
 __global__ void __launch_bounds__(128)
-k_kd_nn_stack(const KdNode *__restrict__ nodes, int n, const double *__restrict__ queries, long long nq,
-              const int *__restrict__ perm, int *__restrict__ idx_out, double *__restrict__ dist_out) {
+k_kd_nn_stack_t(const KdNode *__restrict__ nodes, int n, const double *__restrict__ queries, long long nq,
+                const int *__restrict__ perm, int *__restrict__ idx_out, double *__restrict__ dist_out,
+                const __grid_constant__ KdFanOut fan) {
     const long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (slot >= nq) return;
-    const long long qi = perm ? perm[slot] : slot;
-    if (n <= 0) {
-        idx_out[qi] = -1;
-        dist_out[qi] = INFINITY;
-        return;
-    }
-    const double qx = queries[qi * 3], qy = queries[qi * 3 + 1], qz = queries[qi * 3 + 2];
-    double best = INFINITY;
+    const bool live = slot < nq;
+    if (!kFanOut && !live) return;
+    const long long qi = live ? (perm ? perm[slot] : slot) : 0;
     int bidx = -1;
+    double best = INFINITY;
+    if (live && n > 0) {
+    const double qx = queries[qi * 3], qy = queries[qi * 3 + 1], qz = queries[qi * 3 + 2];
     int st_lo[32], st_hi[32];
     double st_plane[32];
     int sp = 0;
@@ -361,8 +363,49 @@ k_kd_nn_stack(const KdNode *__restrict__ nodes, int n, const double *__restrict_
         }
         if (!found) break;
     }
-    idx_out[qi] = bidx;
-    dist_out[qi] = bidx >= 0 ? __dsqrt_rn(best) : INFINITY;
+    }
+    const double dist = bidx >= 0 ? __dsqrt_rn(best) : INFINITY;
+    if (!kFanOut) {
+        idx_out[qi] = bidx;
+        dist_out[qi] = dist;
+        return;
+    }
+    if (live) {
+        const long long at = fan.q_lo + qi;
+#pragma unroll 1
+        for (int r = 0; r < fan.world; ++r) {
+            fan.idx[r][at] = bidx;
+            fan.dist[r][at] = dist;
+        }
+        __threadfence_system();  // the stores to peer memory are performed before this thread's part in the ticket
+    }
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(fan.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x < fan.world) {
+        __threadfence_system();
+        if (threadIdx.x == 0) *fan.ticket = 0u;
+        *(volatile unsigned long long *)(fan.flags[threadIdx.x] + fan.rank) = fan.seq;  // "rank has delivered call seq"
+    }
+}
+
+// waits until every rank has posted `seq` in this rank's flag slots (local memory; the peers write it);
+// err[0] is set if that takes longer than timeout_ns
+__global__ void k_peer_wait(const unsigned long long *flags, int world, unsigned long long seq, unsigned long long timeout_ns,
+                            unsigned *err) {
+    if ((int)threadIdx.x >= world) return;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*(volatile const unsigned long long *)(flags + threadIdx.x) < seq) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) {
+            atomicExch(err, 1u + threadIdx.x);
+            return;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
 }
 
 cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const double *d_queries, size_t nq,
@@ -392,10 +435,27 @@ cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const d
         return cudaGetLastError();
     }
     if (use_stack)
-        k_kd_nn_stack<<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx, d_dist);
+        k_kd_nn_stack_t<false><<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx, d_dist,
+                                                          KdFanOut{});
     else
         k_kd_nn<<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx, d_dist);
     if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// the query shard [fan.q_lo, fan.q_lo + nq) answered and delivered to every rank's buffer (see KdFanOut)
+cudaError_t kd_nn_fanout(const KdNode *d_nodes, size_t n, const double *d_queries, size_t nq, const KdFanOut &fan,
+                         cudaStream_t stream, uint64_t *launches) {
+    const int threads = 128;
+    // an empty shard still has to post its arrival: one CTA
+    const unsigned grid = (unsigned)((nq + threads - 1) / threads) ? (unsigned)((nq + threads - 1) / threads) : 1u;
+    k_kd_nn_stack_t<true><<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, nullptr, nullptr, fan);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t peer_wait(const unsigned long long *flags, int world, unsigned long long seq, unsigned *err, cudaStream_t stream) {
+    k_peer_wait<<<1, 32, 0, stream>>>(flags, world, seq, 5000000000ull /* 5 s */, err);
     return cudaGetLastError();
 }
 

@@ -136,3 +136,72 @@ def gather_sequence_results(local: Sequence[Tuple[int, np.ndarray]], world: int,
         for sid, arr in part:
             merged[sid] = arr
     return merged
+
+
+class PeerGather:
+    """Config 5b over peer memory (include/navslam_b200.h, nav_peer_*): the answers of every rank's query shard
+    are stored by the search kernel itself into the result buffers of all ranks of the node (CUDA IPC mappings,
+    NVLink stores), so no collective follows the search.  torch.distributed only carries the 64-byte memory
+    handles once, at construction.  Raises NavError when the buffers cannot be mapped (no peer access between the
+    GPUs, or more than eight ranks): callers then use sharded_nn_into()."""
+
+    def __init__(self, lib, device: int, nq_total: int, *, group=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+        from .binding import NavError
+        self.L, self.device, self.nq = lib, device, int(nq_total)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        handle = C.create_string_buffer(64)
+        self.h = lib.nav_peer_create(device, self.nq, handle)
+        if not self.h:
+            raise NavError(lib.nav_last_error().decode())
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, handle.raw, group=group)
+        else:
+            handles[0] = handle.raw
+        rc = lib.nav_peer_connect(self.h, self.world, self.rank, b"".join(handles))
+        ok = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(ok, rc == 0, group=group)   # all ranks use the peer path, or none does
+        else:
+            ok[0] = rc == 0
+        if not all(ok):
+            msg = lib.nav_last_error().decode() if rc else "another rank could not map the peer buffers"
+            self.close()
+            raise NavError(msg)
+
+    def nn(self, tree, queries, stream: int):
+        """queries: [nq_total, 3] float64 CUDA tensor, identical on every rank.  Returns (idx int32 [nq_total],
+        dist float64 [nq_total]) as tensors aliasing this rank's buffer: complete in stream order, valid until the
+        call after the next one."""
+        import ctypes as C
+
+        import torch
+        from .binding import NavError
+        lo, hi = shard_bounds(self.nq, self.world, self.rank)
+        shard = queries[lo:hi]
+        pi, pd = C.c_void_p(), C.c_void_p()
+        rc = self.L.nav_kdtree_nn_allgather_dev(tree.h, self.h, shard.data_ptr(), lo, hi - lo, C.byref(pi), C.byref(pd),
+                                                stream)
+        if rc:
+            raise NavError(self.L.nav_last_error().decode())
+
+        class _Raw:
+            def __init__(self, ptr, n, typestr):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+        dev = queries.device
+        return (torch.as_tensor(_Raw(pi.value, self.nq, "<i4"), device=dev),
+                torch.as_tensor(_Raw(pd.value, self.nq, "<f8"), device=dev))
+
+    def check(self):
+        from .binding import NavError
+        if self.L.nav_peer_check(self.h):
+            raise NavError(self.L.nav_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.nav_peer_destroy(self.h)
+            self.h = None
