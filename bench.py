@@ -1031,6 +1031,28 @@ def kd_legs(args, torch, dist, pkg, stream, world, rank, local, spin_up, barrier
                 nn["weak_scaling"]["peer_memory_error"] = str(ex)[:200]
         del d_qw, wi, wd
     if peer is not None:
+        # the MAP sharded instead of the queries: every rank builds 1/world of the points and searches it for all
+        # queries; partial answers meet at the owners of the queries, merged answers go to everybody (two rounds over
+        # peer memory).  What a map that is rebuilt every frame wants: the build shrinks with the world.
+        try:
+            peer.nq = nq
+            lo_p, hi_p = sharding.shard_bounds(n_map, world, rank)
+            part, pb_ms, pb_launches = time_build(d_pts[lo_p:hi_p].data_ptr(), hi_p - lo_p)
+            si, sd = peer.nn_sharded_map(part, d_q, lo_p, s)
+            torch.cuda.synchronize()
+            same = bool(torch.equal(si[:nq], buf_i) and torch.equal(sd[:nq], buf_d))
+            sm_ms = time_steps(lambda: peer.nn_sharded_map(part, d_q, lo_p, s))
+            peer.check()
+            sm_ms, pb_ms = reduce_max([sm_ms, pb_ms])
+            nn["sharded_map"] = {
+                "workload": "cfg5b with the MAP sharded: %d ranks x %d points, all 131072 queries on every rank, partial "
+                            "answers merged by the owners of the queries over peer memory" % (world, hi_p - lo_p),
+                "build_ms": pb_ms, "build_launches": pb_launches, "query_ms": sm_ms, "queries_per_s": nq / (sm_ms * 1e-3),
+                "same_answers_as_replicated_tree": same,
+                "build_plus_query_ms": pb_ms + sm_ms, "replicated_build_plus_query_ms": b_ms + (peer_ms or q_ms)}
+            part.close()
+        except Exception as ex:  # noqa: BLE001
+            nn["sharded_map"] = {"error": str(ex)[:200]}
         barrier()
         peer.close()
     tree.close()

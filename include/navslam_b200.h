@@ -120,6 +120,13 @@ nav_peer *nav_peer_create(int device, size_t nq_total, unsigned char handle_out[
 int nav_peer_connect(nav_peer *p, int world, int rank, const unsigned char *handles /* world x 64 bytes */);
 int nav_kdtree_nn_allgather_dev(nav_kdtree *tree, nav_peer *p, const void *dev_queries, size_t q_lo, size_t nq_shard,
                                 void **idx_full, void **dist_full, void *cuda_stream);
+/* The MAP sharded instead of the queries (a map that is rebuilt every frame costs each of N ranks the build of
+ * 1/N of it): `tree` holds this rank's part of the points, idx_offset the index of its first point in the whole
+ * map; dev_queries are ALL nq queries (the same on every rank).  Partial answers go to the rank that owns the
+ * query, the owners take the minimum (squared distance, index) -- the pair a search of the whole map keeps -- and
+ * deliver it to every rank: two rounds over peer memory.  Same results as one tree over all points. */
+int nav_kdtree_nn_sharded_map_dev(nav_kdtree *tree, nav_peer *p, const void *dev_queries, size_t nq, int64_t idx_offset,
+                                  void **idx_full, void **dist_full, void *cuda_stream);
 int nav_peer_check(nav_peer *p);   /* after a synchronisation: did every rank deliver every call? */
 void nav_peer_destroy(nav_peer *p);
 /* exact brute force on the same contract.  use_tensor_cores == 0: plain binary64 scan.

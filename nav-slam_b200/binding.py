@@ -55,7 +55,8 @@ EXPORTS = [
     "nav_csv_format_frame_dev", "nav_l5_json_read", "nav_imu_json_read",
     "nav_frontend_submit", "nav_frontend_frame_depth_async", "nav_slam_prefetch", "nav_slam_prefetch_depth",
     "nav_host_register", "nav_host_unregister", "nav_slam_run",
-    "nav_peer_create", "nav_peer_connect", "nav_kdtree_nn_allgather_dev", "nav_peer_check", "nav_peer_destroy",
+    "nav_peer_create", "nav_peer_connect", "nav_kdtree_nn_allgather_dev", "nav_kdtree_nn_sharded_map_dev", "nav_peer_check",
+    "nav_peer_destroy",
 ]
 
 
@@ -137,6 +138,8 @@ def load_library(build_if_missing: bool = True):
     L.nav_peer_connect.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
     L.nav_kdtree_nn_allgather_dev.argtypes = [vp, vp, vp, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p),
                                               C.POINTER(C.c_void_p), vp]
+    L.nav_kdtree_nn_sharded_map_dev.argtypes = [vp, vp, vp, C.c_size_t, C.c_int64, C.POINTER(C.c_void_p),
+                                                C.POINTER(C.c_void_p), vp]
     L.nav_peer_check.argtypes = [vp]
     L.nav_peer_destroy.argtypes = [vp]
     L.nav_slam_prefetch.argtypes = [vp, vp]

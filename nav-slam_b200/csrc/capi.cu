@@ -1789,7 +1789,23 @@ struct nav_peer {
     unsigned long long seq = 0;
 };
 
-static size_t peer_half_bytes(size_t nq_cap) { return nq_cap * 12 + kMaxPeers * 8; }
+// one half (call parity) of a rank's buffer: final dist | final idx | partial dsq | partial idx | flags A | flags B
+struct PeerLayout {
+    size_t dist, idx, pdsq, pidx, flags_a, flags_b, half;
+};
+static PeerLayout peer_layout(size_t nq_cap) {
+    const size_t part = nq_cap + 2 * kMaxPeers;  // world shards of ceil(nq / world) entries, rounded up to even
+    PeerLayout l;
+    l.dist = 0;
+    l.idx = l.dist + nq_cap * 8;
+    l.pdsq = l.idx + nq_cap * 4;
+    l.pidx = l.pdsq + part * 8;
+    l.flags_a = l.pidx + part * 4;
+    l.flags_b = l.flags_a + kMaxPeers * 8;
+    l.half = l.flags_b + kMaxPeers * 8;
+    return l;
+}
+static size_t peer_half_bytes(size_t nq_cap) { return peer_layout(nq_cap).half; }
 
 extern "C" void nav_peer_destroy(nav_peer *p) {
     if (!p) return;
@@ -1870,12 +1886,13 @@ extern "C" int nav_kdtree_nn_allgather_dev(nav_kdtree *t, nav_peer *p, const voi
     t->on_user_stream = true;
     const unsigned long long seq = ++p->seq;
     const size_t off = (seq & 1ull) * p->half;
+    const PeerLayout l = peer_layout(p->nq_cap);
     KdFanOut fan = {};
     for (int r = 0; r < p->world; ++r) {
         unsigned char *b = p->peer[r] + off;
-        fan.dist[r] = (double *)b;
-        fan.idx[r] = (int *)(b + p->nq_cap * 8);
-        fan.flags[r] = (unsigned long long *)(b + p->nq_cap * 12);
+        fan.dist[r] = (double *)(b + l.dist);
+        fan.idx[r] = (int *)(b + l.idx);
+        fan.flags[r] = (unsigned long long *)(b + l.flags_a);
     }
     fan.ticket = (unsigned *)(p->own + 2 * p->half);
     fan.q_lo = (long long)q_lo;
@@ -1883,11 +1900,65 @@ extern "C" int nav_kdtree_nn_allgather_dev(nav_kdtree *t, nav_peer *p, const voi
     fan.world = p->world;
     fan.rank = p->rank;
     CU(kd_nn_fanout(t->d_nodes, t->n, (const double *)dev_queries, nq_shard, fan, s, &t->launches));
-    CU(peer_wait((const unsigned long long *)(p->own + off + p->nq_cap * 12), p->world, seq,
+    CU(peer_wait((const unsigned long long *)(p->own + off + l.flags_a), p->world, seq,
                  (unsigned *)(p->own + 2 * p->half + 4), s));
     t->launches++;
-    *dist_full = p->own + off;
-    *idx_full = p->own + off + p->nq_cap * 8;
+    *dist_full = p->own + off + l.dist;
+    *idx_full = p->own + off + l.idx;
+    return 0;
+}
+
+// The MAP sharded instead of the queries: `t` holds this rank's part of the map points (idx_offset = index of its
+// first point in the whole map).  Every rank searches its part for ALL nq queries (the same array on every rank)
+// and sends each partial answer -- squared distance and global index -- to the rank that owns the query; the owners
+// take the minimum (distance, index), which is the pair a search of the whole map keeps, and deliver it to every
+// rank.  Two exchange rounds over peer memory, no collective; the build of a 10 M-point map costs each of eight
+// ranks the build of 1.25 M points.
+extern "C" int nav_kdtree_nn_sharded_map_dev(nav_kdtree *t, nav_peer *p, const void *dev_queries, size_t nq,
+                                             int64_t idx_offset, void **idx_full, void **dist_full, void *cuda_stream) {
+    if (!t || !p || !idx_full || !dist_full) return fail("nav_kdtree_nn_sharded_map_dev: null argument");
+    if (nq && !dev_queries) return fail("nav_kdtree_nn_sharded_map_dev: null queries");
+    if (nq > p->nq_cap) return fail("nav_kdtree_nn_sharded_map_dev: %zu queries exceed the buffer (%zu)", nq, p->nq_cap);
+    if (idx_offset < 0 || idx_offset + (int64_t)t->n > 0x7fffffffLL) return fail("nav_kdtree_nn_sharded_map_dev: index range");
+    if (t->device != p->device) return fail("nav_kdtree_nn_sharded_map_dev: tree and buffer live on different devices");
+    CU(cudaSetDevice(t->device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    if (t->on_user_stream && t->user_stream != s) CU(cudaStreamSynchronize(t->user_stream));
+    t->user_stream = s;
+    t->on_user_stream = true;
+    const PeerLayout l = peer_layout(p->nq_cap);
+    unsigned *err = (unsigned *)(p->own + 2 * p->half + 4);
+    KdFanOut fan = {};
+    fan.ticket = (unsigned *)(p->own + 2 * p->half);
+    fan.world = p->world;
+    fan.rank = p->rank;
+    fan.nq_total = (long long)nq;
+    fan.shard_cap = (int)(((nq + p->world - 1) / p->world + 1) & ~(size_t)1);
+    fan.idx_offset = (int)idx_offset;
+    long long lo, hi;
+    shard_range((long long)nq, p->world, p->rank, lo, hi);
+    fan.q_lo = lo;
+    // round 1: partial answers to the owners of the queries
+    unsigned long long seq = ++p->seq;
+    size_t off = (seq & 1ull) * p->half;
+    for (int r = 0; r < p->world; ++r) {
+        unsigned char *b = p->peer[r] + off;
+        fan.pdsq[r] = (double *)(b + l.pdsq);
+        fan.pidx[r] = (int *)(b + l.pidx);
+        fan.dist[r] = (double *)(b + l.dist);
+        fan.idx[r] = (int *)(b + l.idx);
+        fan.flags[r] = (unsigned long long *)(b + l.flags_a);
+    }
+    fan.seq = seq;
+    CU(kd_nn_partial(t->d_nodes, t->n, (const double *)dev_queries, nq, fan, s, &t->launches));
+    CU(peer_wait((const unsigned long long *)(p->own + off + l.flags_a), p->world, seq, err, s));
+    // round 2: merge this rank's query shard and deliver it to everybody (same half, second set of flags)
+    for (int r = 0; r < p->world; ++r) fan.flags[r] = (unsigned long long *)(p->peer[r] + off + l.flags_b);
+    CU(peer_merge(fan, s));
+    CU(peer_wait((const unsigned long long *)(p->own + off + l.flags_b), p->world, seq, err, s));
+    t->launches += 3;
+    *dist_full = p->own + off + l.dist;
+    *idx_full = p->own + off + l.idx;
     return 0;
 }
 

@@ -304,7 +304,7 @@ k_kd_nn_conv(const KdNode *__restrict__ nodes, int n, const double *__restrict__
 // kFanOut: the answers of this rank's query shard are written straight into the result buffers of EVERY rank
 // (peer memory over NVLink; nav_kdtree_nn_allgather_dev) -- the all-gather is the kernel's epilogue --, and
 // the CTA that finishes last posts this rank's arrival in every rank's flag slot.
-template <bool kFanOut>
+template <int kFanOut>   // 0: plain, 1: replicated tree + query shard delivered to all ranks, 2: map shard, partials to the owners
 __global__ void __launch_bounds__(128)
 k_kd_nn_stack_t(const KdNode *__restrict__ nodes, int n, const double *__restrict__ queries, long long nq,
                 const int *__restrict__ perm, int *__restrict__ idx_out, double *__restrict__ dist_out,
@@ -371,11 +371,20 @@ k_kd_nn_stack_t(const KdNode *__restrict__ nodes, int n, const double *__restric
         return;
     }
     if (live) {
-        const long long at = fan.q_lo + qi;
+        if (kFanOut == 1) {
+            const long long at = fan.q_lo + qi;
 #pragma unroll 1
-        for (int r = 0; r < fan.world; ++r) {
-            fan.idx[r][at] = bidx;
-            fan.dist[r][at] = dist;
+            for (int r = 0; r < fan.world; ++r) {
+                fan.idx[r][at] = bidx;
+                fan.dist[r][at] = dist;
+            }
+        } else {
+            const int owner = shard_owner(fan.nq_total, fan.world, qi);
+            long long lo, hi;
+            shard_range(fan.nq_total, fan.world, owner, lo, hi);
+            const long long at = (long long)fan.rank * fan.shard_cap + (qi - lo);
+            fan.pdsq[owner][at] = best;   // the squared distance decides the merge, as it decides the search
+            fan.pidx[owner][at] = bidx >= 0 ? bidx + fan.idx_offset : -1;
         }
         __threadfence_system();  // the stores to peer memory are performed before this thread's part in the ticket
     }
@@ -435,7 +444,7 @@ cudaError_t kd_nn(const KdNode *d_nodes, size_t n, const double *d_bbox, const d
         return cudaGetLastError();
     }
     if (use_stack)
-        k_kd_nn_stack_t<false><<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx, d_dist,
+        k_kd_nn_stack_t<0><<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx, d_dist,
                                                           KdFanOut{});
     else
         k_kd_nn<<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, d_idx, d_dist);
@@ -449,8 +458,64 @@ cudaError_t kd_nn_fanout(const KdNode *d_nodes, size_t n, const double *d_querie
     const int threads = 128;
     // an empty shard still has to post its arrival: one CTA
     const unsigned grid = (unsigned)((nq + threads - 1) / threads) ? (unsigned)((nq + threads - 1) / threads) : 1u;
-    k_kd_nn_stack_t<true><<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, nullptr, nullptr, fan);
+    k_kd_nn_stack_t<1><<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, nullptr, nullptr, fan);
     if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// Point-sharded map, second step: this rank owns the query shard [q_lo, q_lo + n_mine); for each of its queries it
+// takes the smallest (squared distance, global index) of the `world` partial answers -- exactly the pair a search of
+// the whole map would keep --, and delivers index and distance to every rank's result arrays; the CTA that finishes
+// last posts the arrival flags of the second round.
+__global__ void __launch_bounds__(128)
+k_peer_merge(const __grid_constant__ KdFanOut fan, long long n_mine) {
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q < n_mine) {
+        double best = INFINITY;
+        int bidx = -1;
+        for (int r = 0; r < fan.world; ++r) {
+            const long long at = (long long)r * fan.shard_cap + q;
+            const double d = __ldcg(fan.pdsq[fan.rank] + at);
+            const int i = __ldcg(fan.pidx[fan.rank] + at);
+            if (i >= 0 && (d < best || (d == best && i < bidx) || bidx < 0)) {
+                best = d;
+                bidx = i;
+            }
+        }
+        const double dist = bidx >= 0 ? __dsqrt_rn(best) : INFINITY;
+#pragma unroll 1
+        for (int r = 0; r < fan.world; ++r) {
+            fan.idx[r][fan.q_lo + q] = bidx;
+            fan.dist[r][fan.q_lo + q] = dist;
+        }
+        __threadfence_system();
+    }
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(fan.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x < fan.world) {
+        __threadfence_system();
+        if (threadIdx.x == 0) *fan.ticket = 0u;
+        *(volatile unsigned long long *)(fan.flags[threadIdx.x] + fan.rank) = fan.seq;
+    }
+}
+
+cudaError_t kd_nn_partial(const KdNode *d_nodes, size_t n, const double *d_queries, size_t nq, const KdFanOut &fan,
+                          cudaStream_t stream, uint64_t *launches) {
+    const int threads = 128;
+    const unsigned grid = (unsigned)((nq + threads - 1) / threads) ? (unsigned)((nq + threads - 1) / threads) : 1u;
+    k_kd_nn_stack_t<2><<<grid, threads, 0, stream>>>(d_nodes, (int)n, d_queries, (long long)nq, nullptr, nullptr, nullptr, fan);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t peer_merge(const KdFanOut &fan, cudaStream_t stream) {
+    long long lo, hi;
+    shard_range(fan.nq_total, fan.world, fan.rank, lo, hi);
+    const long long n_mine = hi - lo;
+    const unsigned grid = (unsigned)((n_mine + 127) / 128) ? (unsigned)((n_mine + 127) / 128) : 1u;
+    k_peer_merge<<<grid, 128, 0, stream>>>(fan, n_mine);
     return cudaGetLastError();
 }
 

@@ -26,7 +26,27 @@ struct KdFanOut {
     long long q_lo;                       // first query of this rank's shard in the full arrays
     unsigned long long seq;               // call number posted to the flag slots
     int world, rank;
+    // point-sharded map (mode 2): every rank searches ITS part of the map for ALL queries and sends each partial
+    // answer (squared distance, global point index) to the rank that owns the query, slot [sender][query - owner.lo]
+    double *pdsq[kMaxPeers];              // rank r's partial squared distances [world][shard_cap]
+    int *pidx[kMaxPeers];                 // rank r's partial indices           [world][shard_cap]
+    long long nq_total;
+    int shard_cap, idx_offset;
 };
+// the contiguous shard [lo, hi) of rank r of n items (first n % world ranks get one more), nav-slam_b200/sharding.py
+__host__ __device__ inline void shard_range(long long n, int world, int r, long long &lo, long long &hi) {
+    const long long base = n / world, extra = n % world;
+    lo = r * base + (r < extra ? r : extra);
+    hi = lo + base + (r < extra ? 1 : 0);
+}
+__host__ __device__ inline int shard_owner(long long n, int world, long long i) {
+    const long long base = n / world, extra = n % world;
+    if (i < (base + 1) * extra) return (int)(i / (base + 1));
+    return (int)(extra + (i - (base + 1) * extra) / (base > 0 ? base : 1));
+}
+cudaError_t kd_nn_partial(const KdNode *d_nodes, size_t n, const double *d_queries, size_t nq, const KdFanOut &fan,
+                          cudaStream_t stream, uint64_t *launches);
+cudaError_t peer_merge(const KdFanOut &fan, cudaStream_t stream);
 cudaError_t kd_nn_fanout(const KdNode *d_nodes, size_t n, const double *d_queries, size_t nq, const KdFanOut &fan,
                          cudaStream_t stream, uint64_t *launches);
 cudaError_t peer_wait(const unsigned long long *flags, int world, unsigned long long seq, unsigned *err, cudaStream_t stream);

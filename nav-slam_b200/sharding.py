@@ -196,6 +196,26 @@ class PeerGather:
         return (torch.as_tensor(_Raw(pi.value, self.nq, "<i4"), device=dev),
                 torch.as_tensor(_Raw(pd.value, self.nq, "<f8"), device=dev))
 
+    def nn_sharded_map(self, tree_part, queries, idx_offset: int, stream: int):
+        """The map sharded instead of the queries: tree_part holds this rank's points (points idx_offset ... of the
+        whole map), queries are all nq_total queries on every rank.  Same return value and answers as nn()."""
+        import ctypes as C
+
+        import torch
+        from .binding import NavError
+        pi, pd = C.c_void_p(), C.c_void_p()
+        rc = self.L.nav_kdtree_nn_sharded_map_dev(tree_part.h, self.h, queries.data_ptr(), self.nq, int(idx_offset),
+                                                  C.byref(pi), C.byref(pd), stream)
+        if rc:
+            raise NavError(self.L.nav_last_error().decode())
+
+        class _Raw:
+            def __init__(self, ptr, n, typestr):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+        dev = queries.device
+        return (torch.as_tensor(_Raw(pi.value, self.nq, "<i4"), device=dev),
+                torch.as_tensor(_Raw(pd.value, self.nq, "<f8"), device=dev))
+
     def check(self):
         from .binding import NavError
         if self.L.nav_peer_check(self.h):

@@ -51,6 +51,26 @@ def main():
         sharding.sharded_nn_into(nn_into, d_q, bi, bd)
         torch.cuda.synchronize()
         assert torch.equal(bi, idx) and torch.equal(bd, dd)
+        # the MAP sharded: every rank builds a tree over its part of the points; same answers, also with clustered
+        # points and exact duplicates across the shard boundary (the merge breaks ties on the global index)
+        for variant in ("uniform", "dup"):
+            mp = pts if variant == "uniform" else np.repeat(pts[: n // 4], 4, axis=0)
+            lo, hi = sharding.shard_bounds(mp.shape[0], world, rank)
+            d_part = torch.from_numpy(np.ascontiguousarray(mp[lo:hi])).cuda()
+            part = nav.KdTree(dev_ptr=d_part.data_ptr(), n=hi - lo, device=local, stream=s)
+            for call in range(3):
+                q = nav.synth.map_queries(mp, nq, seed=200 + call)
+                if variant == "dup":
+                    q[: nq // 2] = mp[np.random.default_rng(call).integers(0, mp.shape[0], nq // 2)]   # exact hits: ties
+                d_q2 = torch.from_numpy(q).cuda()
+                idx, dd = pg.nn_sharded_map(part, d_q2, lo, s)
+                torch.cuda.synchronize()
+                oi, od = oracle.nn_brute(mp, q)
+                assert np.array_equal(idx.cpu().numpy(), oi), (rank, nq, variant, call)
+                assert np.array_equal(dd.cpu().numpy(), od), (rank, nq, variant, call)
+            pg.check()
+            dist.barrier()
+            part.close()
         dist.barrier()
         pg.close()
     tree.close()
