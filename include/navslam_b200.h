@@ -116,6 +116,9 @@ int nav_kdtree_nn_batch_dev(nav_kdtree *tree, const void *dev_queries, size_t nq
  * idx / dist (device pointers into this rank's buffer) hold the answers of ALL queries once the stream has
  * passed the call; they stay valid until the call after the next one.  world <= 8. */
 typedef struct nav_peer nav_peer;
+/* contiguous shard [lo, hi) of rank `rank` of n items (the first n % world ranks hold one more), and its inverse */
+void nav_shard_range(int64_t n, int world, int rank, int64_t *lo, int64_t *hi);
+int nav_shard_owner(int64_t n, int world, int64_t i);
 nav_peer *nav_peer_create(int device, size_t nq_total, unsigned char handle_out[64]);
 int nav_peer_connect(nav_peer *p, int world, int rank, const unsigned char *handles /* world x 64 bytes */);
 int nav_kdtree_nn_allgather_dev(nav_kdtree *tree, nav_peer *p, const void *dev_queries, size_t q_lo, size_t nq_shard,

@@ -56,7 +56,7 @@ EXPORTS = [
     "nav_frontend_submit", "nav_frontend_frame_depth_async", "nav_slam_prefetch", "nav_slam_prefetch_depth",
     "nav_host_register", "nav_host_unregister", "nav_slam_run",
     "nav_peer_create", "nav_peer_connect", "nav_kdtree_nn_allgather_dev", "nav_kdtree_nn_sharded_map_dev", "nav_peer_check",
-    "nav_peer_destroy",
+    "nav_peer_destroy", "nav_shard_range", "nav_shard_owner",
 ]
 
 
@@ -140,6 +140,9 @@ def load_library(build_if_missing: bool = True):
                                               C.POINTER(C.c_void_p), vp]
     L.nav_kdtree_nn_sharded_map_dev.argtypes = [vp, vp, vp, C.c_size_t, C.c_int64, C.POINTER(C.c_void_p),
                                                 C.POINTER(C.c_void_p), vp]
+    L.nav_shard_range.restype = None
+    L.nav_shard_range.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.nav_shard_owner.argtypes = [C.c_int64, C.c_int, C.c_int64]
     L.nav_peer_check.argtypes = [vp]
     L.nav_peer_destroy.argtypes = [vp]
     L.nav_slam_prefetch.argtypes = [vp, vp]

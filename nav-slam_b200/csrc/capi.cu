@@ -1774,6 +1774,16 @@ extern "C" int nav_kdtree_nn_batch_dev(nav_kdtree *t, const void *dev_queries, s
     return 0;
 }
 
+// the shard arithmetic the peer-memory kernels use (host copies, for the tests: it must agree with
+// nav-slam_b200/sharding.py shard_bounds on every rank)
+extern "C" void nav_shard_range(int64_t n, int world, int rank, int64_t *lo, int64_t *hi) {
+    long long a = 0, b = 0;
+    shard_range((long long)n, world, rank, a, b);
+    if (lo) *lo = a;
+    if (hi) *hi = b;
+}
+extern "C" int nav_shard_owner(int64_t n, int world, int64_t i) { return shard_owner((long long)n, world, (long long)i); }
+
 // ------------------------------------------------------------------ peer-memory exchange -----
 // Config 5b (queries sharded across the GPUs of a node against a replicated tree): instead of a collective
 // behind the search, every rank's search kernel writes its shard's answers straight into the result buffers of

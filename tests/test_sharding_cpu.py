@@ -37,3 +37,20 @@ def test_world_size_2_gloo():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "rank 0 ok" in res.stdout and "rank 1 ok" in res.stdout
+
+
+def test_library_shard_arithmetic_agrees_with_python():
+    """The peer-memory kernels route answers with nav_shard_range / nav_shard_owner (csrc/nav_kdtree.cuh); the Python
+    side cuts the queries with sharding.shard_bounds.  Host functions: no GPU needed."""
+    import ctypes as C
+    nav = importlib.import_module("nav-slam_b200")
+    L = nav.load_library()
+    for n in (0, 1, 7, 8, 9, 1001, 131072, 131073):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                lo, hi = C.c_int64(), C.c_int64()
+                L.nav_shard_range(n, world, r, C.byref(lo), C.byref(hi))
+                assert (lo.value, hi.value) == sharding.shard_bounds(n, world, r)
+                for i in {lo.value, (lo.value + hi.value) // 2, hi.value - 1}:
+                    if lo.value <= i < hi.value:
+                        assert L.nav_shard_owner(n, world, i) == r
