@@ -948,3 +948,66 @@ def test_slam_run_with_a_prediction_callback_and_registered_memory(pkg, synth):
     rc = L.nav_slam_run(ctx.h, ptrs, n - 1, 0, cb, None, None, C.byref(start), out, None, None)
     assert rc != 0 and b"pinned" in L.nav_last_error()
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_long_sequence_launch_equals_per_frame_launches(pkg, synth):
+    """70 frames in one nav_frontend_sequence_dev call (longer than the 64 frames whose poses fit the kernel
+    parameters: the poses are uploaded) leave exactly what 70 nav_frontend_frame_dev calls leave -- labels, NN of the
+    last frame, final map -- and the same again on a second run (no race between the tiles of a row's cluster)."""
+    torch = pytest.importorskip("torch")
+    r, c, n = 16, 1800, 71
+    frames = np.stack([synth.room_frame(r, c, f % 23) for f in range(n)])     # 23 distinct frames, back and forth
+    d_frames = torch.from_numpy(frames).cuda()
+    stream = torch.cuda.Stream()
+    pose = lambda f: np.array([50.0 * (f % 23), 0.3 * (f % 5), 0, 0, 0, 0.1 * (f % 3)])
+    final = np.stack([pose(f) for f in range(n)])
+    last = np.concatenate([np.zeros((1, 6)), final[:-1]])
+    pred = final + np.array([-1.5, 0.7, 0.2, 0, 0, 0.05])
+    ctx = pkg.Context(r, c, device=0)
+    ctx.set_stream(stream.cuda_stream)
+    npx = r * c
+
+    def grab():
+        stream.synchronize()
+        res = ctx.frame_results_dev()
+        return (_dev_to_numpy(torch, res.labels, np.int32, npx), _dev_to_numpy(torch, res.nn_idx, np.int32, npx),
+                _dev_to_numpy(torch, res.nn_dist, np.float64, npx), _dev_to_numpy(torch, res.global_, np.float64, npx * 3))
+    runs = []
+    for rep in range(2):
+        ctx.slam_init_dev(d_frames[0].data_ptr(), np.zeros(6))
+        ctx.frontend_sequence_dev(d_frames[1].data_ptr(), n - 1, pred[1:], last[1:], final[1:])
+        runs.append(grab())
+    ctx.slam_init_dev(d_frames[0].data_ptr(), np.zeros(6))
+    for f in range(1, n):
+        ctx.frontend_frame_dev(d_frames[f].data_ptr(), pred[f], last[f], final[f])
+    want = grab()
+    for got in runs:
+        lab = want[0] == 1
+        assert np.array_equal(got[0], want[0])
+        assert np.array_equal(got[1][lab], want[1][lab]) and np.array_equal(got[2][lab], want[2][lab])
+        assert np.array_equal(got[3], want[3])
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["uniform", "room"])
+def test_kdtree_build_is_deterministic(pkg, synth, kind):
+    """The build places elements with atomic counters, but the node of a range is a function of the SET of points in
+    it: repeated builds give the same node array bit for bit (uniform points; a map of plane surfaces, which takes the
+    second selection round and the two-level counting sort)."""
+    if kind == "uniform":
+        pts = synth.map_points(300000, seed=3)
+    else:
+        pts, _ = synth.accumulated_map(2, rows=64, cols=2048)
+    first = None
+    for rep in range(3):
+        tree = pkg.KdTree(pts, device=0)
+        nodes, oidx, axes = tree.export(with_axes=True)
+        tree.close()
+        if first is None:
+            first = (nodes, oidx, axes)
+            assert np.array_equal(np.sort(oidx), np.arange(pts.shape[0]))
+            _check_inorder(nodes, axes, 0, pts.shape[0], 0, "widest")
+        else:
+            assert np.array_equal(nodes, first[0]) and np.array_equal(oidx, first[1]) and np.array_equal(axes, first[2])
