@@ -19,12 +19,14 @@ ncu --set full --clock-control none --import-source on -k "regex:k_loop_step" -s
 python profiles/ncu_table.py $O/r2_loop_step.ncu-rep > $O/r2_loop_step.txt 2>&1
 # kd build: time per call, then every launch of one 1 M build with its DRAM bytes (per-level traffic)
 python profiles/prof_kdbuild.py > $O/r2_kdbuild.txt 2>&1
-ncu --set full --clock-control none -k "regex:k_kd_" -s 48 -c 24 -f -o $O/r2_kdbuild_levels python profiles/prof_kdbuild.py 1000000 > $O/ncu_kdb.log 2>&1
+ncu --set full --clock-control none -k "regex:k_kd_" -s 60 -c 30 -f -o $O/r2_kdbuild_levels python profiles/prof_kdbuild.py 1000000 > $O/ncu_kdb.log 2>&1
 python profiles/ncu_kernels.py $O/r2_kdbuild_levels.ncu-rep > $O/r2_kdbuild_levels.txt 2>&1
 python profiles/prof_frame.py > $O/r2_frame_us.txt 2>&1
 NAV_SEQ_LAUNCHES=1 python profiles/prof_frame.py >> $O/r2_frame_us.txt 2>&1
 python profiles/prof_stencil.py 1000 5 > $O/r2_stencil_1000_frames.txt 2>&1
 python profiles/prof_nn.py 1024 4096 16384 65536 1000000 10000000 > $O/r2_nn_sizes.txt 2>&1
 python profiles/prof_pcie.py > $O/r2_pcie.txt 2>&1
+python profiles/prof_nn_frame.py > $O/r2_nn_frame.txt 2>&1
+python profiles/sass_opcodes.py > $O/r2_sass_opcodes.txt 2>&1
 rm -f $O/*.ncu-rep.tmp
 ls -la $O | tail -30
