@@ -155,13 +155,18 @@ class PeerGather:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         handle = C.create_string_buffer(64)
         self.h = lib.nav_peer_create(device, self.nq, handle)
-        if not self.h:
-            raise NavError(lib.nav_last_error().decode())
+        # every step that can fail on one rank is followed by an exchange of the outcome, so that all ranks raise
+        # together instead of one leaving the others inside a collective
         handles = [None] * self.world
+        mine = handle.raw if self.h else None
         if self.world > 1:
-            dist.all_gather_object(handles, handle.raw, group=group)
+            dist.all_gather_object(handles, mine, group=group)
         else:
-            handles[0] = handle.raw
+            handles[0] = mine
+        if any(h is None for h in handles):
+            msg = lib.nav_last_error().decode() if not self.h else "another rank could not allocate its peer buffer"
+            self.close()
+            raise NavError(msg)
         rc = lib.nav_peer_connect(self.h, self.world, self.rank, b"".join(handles))
         ok = [None] * self.world
         if self.world > 1:
