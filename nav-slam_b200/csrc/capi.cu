@@ -1978,7 +1978,7 @@ extern "C" int nav_peer_check(nav_peer *p) {
     CU(cudaSetDevice(p->device));
     unsigned err = 0;
     CU(cudaMemcpy(&err, p->own + 2 * p->half + 4, 4, cudaMemcpyDeviceToHost));
-    if (err) return fail("nav_peer: rank %u did not deliver within 5 s", err - 1u);
+    if (err) return fail("nav_peer: rank %u did not deliver within 30 s", err - 1u);
     return 0;
 }
 

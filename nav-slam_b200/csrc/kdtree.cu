@@ -520,7 +520,7 @@ cudaError_t peer_merge(const KdFanOut &fan, cudaStream_t stream) {
 }
 
 cudaError_t peer_wait(const unsigned long long *flags, int world, unsigned long long seq, unsigned *err, cudaStream_t stream) {
-    k_peer_wait<<<1, 32, 0, stream>>>(flags, world, seq, 5000000000ull /* 5 s */, err);
+    k_peer_wait<<<1, 32, 0, stream>>>(flags, world, seq, 30000000000ull /* 30 s */, err);
     return cudaGetLastError();
 }
 
