@@ -569,6 +569,26 @@ __device__ __forceinline__ void cluster_sync_all() {
 // labels (a3), query transform (a7), exact search of the row map of the previous frame (a6), the next map from
 // the frame's final pose into the other map buffer (a7, a4/a5).  labels / nn_idx / nn_dist hold the results of
 // the last frame, as after the same number of separate launches.
+#ifdef NAV_SEQ_TIMING
+// developer instrumentation (profiles/prof_seq_phases.py; build rowmap.cu with -DNAV_SEQ_TIMING): thread 0 of every
+// CTA stamps %globaltimer at seven points of every frame of k_frame_seq
+__device__ unsigned long long *g_seq_stamps;   // [frames][ctas][8]
+#define NAV_STAMP(k)                                                                                              \
+    do {                                                                                                          \
+        if (threadIdx.x == 0 && g_seq_stamps) {                                                                   \
+            unsigned long long t_;                                                                                \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                               \
+            const int cta_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;                      \
+            g_seq_stamps[((long long)f * gridDim.x * gridDim.y * gridDim.z + cta_) * 8 + (k)] = t_;               \
+        }                                                                                                         \
+    } while (0)
+extern "C" int nav_debug_set_seq_stamps(void *dev_ptr) {
+    return (int)cudaMemcpyToSymbol(g_seq_stamps, &dev_ptr, sizeof(void *));
+}
+#else
+#define NAV_STAMP(k)
+#endif
+
 constexpr int kSeqInlineFrames = 64;
 struct SeqArgs {
     const double *frames;     // [n_frames][n_seq*rows][cols][3]
@@ -602,6 +622,7 @@ k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, Match
     tile_stage_async(s_pts[0], a.frames + base * 3, c0, cols);
     cp_async_commit();
     for (int f = 0; f < a.n_frames; ++f) {
+        NAV_STAMP(0);
         const double *pts = s_pts[f & 1];
         const RowMap &map = (f & 1) ? map1 : map0;
         const RowMap &map_next = (f & 1) ? map0 : map1;
@@ -610,11 +631,14 @@ k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, Match
                             map.n_chunks, map.n_super, tile * kChunksPerSuper - 1};
         cp_async_wait_group<0>();  // this frame's tile has landed
         __syncthreads();
+        NAV_STAMP(1);
         // the labels need nothing from the row's other tiles: they are computed BEFORE waiting for the cluster
         // (the barrier was only signalled at the end of the previous frame), which turns the wait for the row's
         // slowest tile into useful time
         const int label = tile_labels_filtered(pts, s_f1, s_f2, c0, cols, n_exact);
+        NAV_STAMP(2);
         if (f > 0) cluster_wait_all();  // the row's map of the previous frame is complete (also a CTA barrier)
+        NAV_STAMP(3);
         prefetch_neighbourhood<true>(sm, rv, cols);
         cp_async_commit();
         // the next frame's tile starts its way from HBM now and has the whole search to arrive
@@ -639,11 +663,13 @@ k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, Match
             map_tile(label == 1, c < cols, own, kInline ? ip.fin[f] : a.pose_fin[(long long)f * a.n_seq + seq], map_next, rid,
                      tile, c, base, s_lo, s_hi);
         }
+        NAV_STAMP(4);
         cp_async_wait_group<1>();  // the neighbourhood of the map; the next tile may still be in flight
         int nq;
         const int slot = block_excl_count(label == 1, s_warp, nq);  // its barriers also publish the prefetch
         if (label == 1) s_qcol[slot] = threadIdx.x;
         __syncthreads();
+        NAV_STAMP(5);
         if ((int)(threadIdx.x & ~31u) < nq) {  // warps with at least one query; spare lanes repeat the last one
             const int t = s_qcol[min((int)threadIdx.x, nq - 1)];
             const int qc = c0 + t;
@@ -661,6 +687,7 @@ k_frame_seq(SeqArgs a, int *__restrict__ labels, RowMap map0, RowMap map1, Match
         }
         // this CTA's part of the row's next map is written and it no longer reads the current one: signal the
         // cluster (release) and go on; the matching wait sits in front of the next frame's map prefetch
+        NAV_STAMP(6);
         cluster_arrive_all();
     }
     cluster_wait_all();  // every arrive has its wait
